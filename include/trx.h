@@ -1,0 +1,128 @@
+/*
+ * trx.h -- C ABI of the B200-native exact flat-index top-k engine (libtrx.so).
+ *
+ * This is the drop-in boundary for TextReact's retrieval hot path.  Every entry point
+ * replaces one call the reference makes into the third-party `faiss` object
+ * (reference = thomas0809/textreact; file:line relative to its root):
+ *
+ *   trx_create      <- faiss.IndexFlatL2(d)          retrieve/retrieve_faiss.py:65
+ *                      (faiss.IndexFlatIP(d) for the 768-d neural retriever, README.md:44-47)
+ *   trx_add         <- index.add(train_fps)           retrieve/retrieve_faiss.py:66
+ *   trx_search      <- index.search(query_fps, k)     retrieve/retrieve_faiss.py:71
+ *   trx_set_groups  <- gold-removed mode, lifted from the consumer-side filter
+ *                      `skip_gold_neighbor`           textreact/dataset.py:74-76
+ *   trx_reset / trx_destroy <- lifetime of the index object built per split
+ *                                                     retrieve/retrieve_faiss.py:62-74
+ *   trx_merge_topk  <- (no reference counterpart) k-way merge of per-shard results for
+ *                      the row-sharded multi-GPU mode
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions, never abort(): every call returns an int
+ *     status (TRX_OK == 0) and leaves a message retrievable with trx_last_error()
+ *     (thread-local).
+ *   - `x`, `xq`, `excl`, `g`, `D`, `I` may each be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes).  Host-pointer calls are synchronous on return;
+ *     device-pointer calls are ordered on `stream` and additionally synchronised before
+ *     return only when the exact-fallback path has to be consulted.
+ *   - the caller owns every buffer it passes; the index owns its device copies
+ *     (fp32 corpus, bf16 corpus, norms, groups, workspaces) until reset/destroy.
+ *   - results: best first (IP: larger score; L2: smaller squared distance), ties by
+ *     ascending id, ids are add-order row numbers (+ id offset), unfilled slots
+ *     I = -1, D = -FLT_MAX (IP) / +FLT_MAX (L2).
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x
+ *     trx_create fails with TRX_ENODEV.
+ */
+#ifndef TRX_H_
+#define TRX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRX_OK 0
+#define TRX_EINVAL 1  /* bad shape / argument */
+#define TRX_ENOMEM 2  /* device (or pinned host) allocation failed */
+#define TRX_ECUDA 3   /* CUDA runtime / driver error (message has the string) */
+#define TRX_ENODEV 4  /* no usable sm_100 device */
+
+#define TRX_METRIC_INNER_PRODUCT 0 /* == faiss.METRIC_INNER_PRODUCT */
+#define TRX_METRIC_L2 1            /* == faiss.METRIC_L2 */
+
+/* trx_set_option("path", v) values */
+#define TRX_PATH_AUTO 0   /* pick by batch size (default) */
+#define TRX_PATH_EXACT 1  /* fp32 streaming scan + exact select (the certified fallback) */
+#define TRX_PATH_STREAM 2 /* bf16 CUDA-core streaming prefilter + fp32 rescore */
+#define TRX_PATH_UMMA 3   /* bf16 tcgen05/TMEM prefilter + fp32 rescore */
+
+typedef struct trx_index trx_index;
+
+typedef struct trx_stats_t {
+    int64_t searches;          /* trx_search calls */
+    int64_t queries;           /* query rows processed */
+    int64_t queries_exact;     /* rows answered by the exact fp32 scan (fallback or forced) */
+    int64_t queries_uncert;    /* rows whose bf16 prefilter failed the exactness certificate */
+    int64_t queries_overflow;  /* rows whose candidate list overflowed */
+    int64_t rescored;          /* candidate rows rescored in fp32 */
+    int64_t candidates;        /* candidates emitted by the prefilter */
+    int32_t last_path;         /* TRX_PATH_* taken by the last batch */
+    int32_t sm_count;
+    int64_t launches;          /* kernels of ours launched so far */
+    double last_prefilter_ms;  /* device time of the dominant scoring kernel, last batch
+                                  (only measured when option "timing" is 1) */
+    double last_total_ms;      /* device time of the whole last batch (same condition) */
+} trx_stats_t;
+
+/* Create an empty flat index of dimension d on CUDA device `device`. */
+int trx_create(int d, int metric, int device, trx_index** out);
+
+/* Append n rows of d floats (row-major, contiguous). */
+int trx_add(trx_index* idx, const float* x, int64_t n);
+
+/* Pre-size the device buffers for `n` total rows (optional; avoids regrowth copies). */
+int trx_reserve(trx_index* idx, int64_t n);
+
+/* Per-row exclusion group (text-dedup group / patent id), n must equal ntotal. */
+int trx_set_groups(trx_index* idx, const int32_t* g, int64_t n);
+
+/* k nearest rows for each of nq queries.  excl (nullable): per-query group to exclude,
+ * -1 = none; requires trx_set_groups.  D: float[nq*k], I: int64[nq*k]. */
+int trx_search(trx_index* idx, const float* xq, int64_t nq, int k, const int32_t* excl,
+               float* D, int64_t* I, void* cuda_stream);
+
+/* Remove all rows (keeps d / metric / options). */
+int trx_reset(trx_index* idx);
+void trx_destroy(trx_index* idx);
+
+int64_t trx_ntotal(const trx_index* idx);
+int trx_dim(const trx_index* idx);
+int trx_metric(const trx_index* idx);
+
+/* Added to every returned id: the first global row of this shard (row-sharded mode). */
+int trx_set_id_offset(trx_index* idx, int64_t offset);
+
+/* Tunables: "path" (TRX_PATH_*), "max_batch", "target_candidates", "sample_rate",
+ * "stream_max_batch" (crossover below which AUTO uses the streaming kernel), "timing". */
+int trx_set_option(trx_index* idx, const char* key, double value);
+int trx_get_option(const trx_index* idx, const char* key, double* value);
+
+int trx_stats(const trx_index* idx, trx_stats_t* out);
+
+/* K-way merge of G per-shard results (each [nq,k], best first, global ids) into one.
+ * Dg: float[G*nq*k], Ig: int64[G*nq*k], shard-major.  Device pointers, stream-ordered. */
+int trx_merge_topk(int metric, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k,
+                   float* D, int64_t* I, void* cuda_stream);
+
+/* Raw bf16 scoring GEMM on the tcgen05 path, for tests and profiling:
+ * out[nq, n] = bf16(xq) . bf16(x_row)  (fp32 accumulate) over rows [row0, row0+n). */
+int trx_debug_scores_umma(trx_index* idx, const float* xq, int64_t nq, int64_t row0, int64_t n,
+                          float* out, void* cuda_stream);
+
+const char* trx_last_error(void);
+const char* trx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRX_H_ */

@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle, north_star rule:
+ids identical wherever the fp64 rank gap exceeds 1e-5 relative, scores within 1e-5."""
+import numpy as np
+import pytest
+
+from oracle import cpu_flat as oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+IP, L2 = 0, 1
+
+
+def _engine():
+    import textreact_b200 as trx
+    return trx
+
+
+def _run(xb, xq, k, metric, path, groups=None, exclude=None, **opts):
+    trx = _engine()
+    idx = trx.IndexFlat(xb.shape[1], metric)
+    idx.add(xb)
+    idx.set_option("path", path)
+    for key, v in opts.items():
+        idx.set_option(key, v)
+    if groups is not None:
+        idx.set_groups(groups)
+    D, I = idx.search(xq, k, exclude=exclude)
+    st = idx.stats()
+    idx.close()
+    return D, I, st
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("shape", [(1000, 64, 7, 10), (5000, 100, 33, 20), (3001, 768, 5, 100)])
+def test_exact_path_small(metric, shape):
+    n, d, nq, k = shape
+    xb, xq = util.gaussian(n, d, 1), util.gaussian(nq, d, 2)
+    D, I, st = _run(xb, xq, k, metric, _engine().PATH_EXACT)
+    oracle.check_parity(D, I, xb, xq, k, metric)
+    assert st["queries_exact"] == nq
+
+
+def test_umma_raw_scores_match_bf16_matmul():
+    """K2 in STORE mode against torch: validates TMA swizzle, UMMA descriptors, TMEM readout."""
+    import torch
+    trx = _engine()
+    n, d, nq = 20000, 768, 300
+    xb, xq = util.gaussian(n, d, 3), util.gaussian(nq, d, 4)
+    idx = trx.IndexFlatIP(d)
+    idx.add(xb)
+    got = idx.debug_scores_umma(torch.from_numpy(xq).cuda(), 256, n - 256 - 77).cpu().numpy()
+    idx.close()
+    ref = (torch.from_numpy(xq).bfloat16().double() @ torch.from_numpy(xb[256:n - 77]).bfloat16().double().T).numpy()
+    err = np.abs(got - ref).max()
+    assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("path_name", ["stream", "umma"])
+def test_prefilter_paths_gaussian(metric, path_name):
+    trx = _engine()
+    path = {"stream": trx.PATH_STREAM, "umma": trx.PATH_UMMA}[path_name]
+    n, d, k = 60000, 768, 20
+    nq = 6 if path_name == "stream" else 300
+    xb, xq = util.gaussian(n, d, 5), util.gaussian(nq, d, 6)
+    D, I, st = _run(xb, xq, k, metric, path)
+    oracle.check_parity(D, I, xb, xq, k, metric)
+    assert st["last_path"] == path
+    assert st["queries_exact"] <= nq // 10, st      # the certificate should hold for almost all
+
+
+def test_config1_c1_shape():
+    """BASELINE.json configs[0]: 100K x 768 fp32 corpus, 1K queries, k=20, inner product."""
+    trx = _engine()
+    xb, xq = util.gaussian(100_000, 768, 11), util.gaussian(1000, 768, 12)
+    D, I, st = _run(xb, xq, 20, IP, trx.PATH_AUTO)
+    Do, Io = oracle.search_blas(xb, xq, 20, IP)
+    # fp32-vs-fp32 agreement with the FAISS restatement, then the fp64 rule on a slice
+    assert (I == Io).mean() > 0.999
+    np.testing.assert_allclose(D, Do, rtol=2e-5, atol=2e-4)
+    oracle.check_parity(D[:64], I[:64], xb, xq[:64], 20, IP)
+    assert st["last_path"] == trx.PATH_UMMA
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_clustered_unit_k100(metric):
+    trx = _engine()
+    xb, xq = util.clustered_unit(50000, 768, 21), util.clustered_unit(200, 768, 22)
+    D, I, st = _run(xb, xq, 100, metric, trx.PATH_UMMA)
+    oracle.check_parity(D, I, xb, xq, 100, metric)
+
+
+@pytest.mark.parametrize("path_name", ["exact", "stream", "umma"])
+def test_fingerprint_l2_ties(path_name):
+    """In-tree workload: 0/1 Morgan bits, d=1024, L2, k=20 (retrieve_faiss.py:36-44, :65, :70)."""
+    trx = _engine()
+    path = {"exact": trx.PATH_EXACT, "stream": trx.PATH_STREAM, "umma": trx.PATH_UMMA}[path_name]
+    xb = util.fingerprints(30000, 1024, 31)
+    xq = xb[:40]                                   # train->train self retrieval (:114-115)
+    D, I, st = _run(xb, xq, 20, L2, path)
+    assert (I[:, 0] >= 0).all() and (D[:, 0] == 0).all()
+    Do, Io = oracle.search_seq(xb, xq, 20, L2)
+    np.testing.assert_array_equal(D, Do)           # integer distances: bit exact
+    np.testing.assert_array_equal(I, Io)           # ties broken by ascending id on both sides
+
+
+def test_int64_count_fingerprints_l2():
+    trx = _engine()
+    xb = util.count_fingerprints(20000, 2048, 41)
+    xq = util.count_fingerprints(50, 2048, 42)
+    D, I, st = _run(xb, xq, 20, L2, trx.PATH_AUTO)
+    Do, Io = oracle.search_seq(xb, xq, 20, L2)
+    np.testing.assert_array_equal(D, Do)
+    np.testing.assert_array_equal(I, Io)
+
+
+@pytest.mark.parametrize("path_name", ["exact", "umma"])
+def test_exclusion_mask_equals_post_filter(path_name):
+    """masked_search(k) == post_filter(search(k + g)) -- textreact/dataset.py:74-76 semantics."""
+    trx = _engine()
+    path = {"exact": trx.PATH_EXACT, "umma": trx.PATH_UMMA}[path_name]
+    n, d, nq, k, g = 40000, 768, 64, 20, 5
+    xb, xq = util.clustered_unit(n, d, 51), util.clustered_unit(nq, d, 52)
+    groups = (np.arange(n) // g).astype(np.int32)
+    rng = np.random.default_rng(53)
+    excl = groups[rng.integers(0, n, nq)].copy()
+    excl[::7] = -1
+    D, I, _ = _run(xb, xq, k, IP, path, groups=groups, exclude=excl)
+    D2, I2, _ = _run(xb, xq, k + g, IP, path)
+    for i in range(nq):
+        keep = [j for j in range(k + g) if groups[I2[i, j]] != excl[i]][:k]
+        np.testing.assert_array_equal(I[i], I2[i, keep])
+        np.testing.assert_array_equal(D[i], D2[i, keep])
+    oracle.check_parity(D, I, xb, xq, k, IP, groups, excl)
+
+
+def test_edge_cases():
+    trx = _engine()
+    d = 32
+    xb = util.gaussian(50, d, 61)
+    idx = trx.IndexFlatIP(d)
+    D, I = idx.search(util.gaussian(3, d, 62), 5)          # empty index
+    assert (I == -1).all() and (D == -oracle.FLT_MAX).all()
+    idx.add(xb[:20]); idx.add(xb[20:])                     # incremental add
+    assert idx.ntotal == 50
+    xq = util.gaussian(4, d, 63)
+    D, I = idx.search(xq, 64)                              # k > ntotal -> -1 padding
+    oracle.check_parity(D, I, xb, xq, 64, IP)
+    D, I = idx.search(xq[:1], 1)                           # nq = 1, k = 1
+    oracle.check_parity(D, I, xb, xq[:1], 1, IP)
+    with pytest.raises(AssertionError):
+        idx.search(util.gaussian(2, d + 1, 64), 3)         # wrong dimension (FAISS: AssertionError)
+    idx.reset()
+    assert idx.ntotal == 0
+    idx.close()
+
+
+def test_duplicate_rows_tie_order():
+    trx = _engine()
+    base = util.gaussian(500, 64, 71)
+    xb = np.concatenate([base, base, base])                # every row three times
+    xq = base[:9]
+    for path in (trx.PATH_EXACT,):
+        D, I, _ = _run(xb, xq, 6, IP, path)
+        Do, Io = oracle.search_seq(xb, xq, 6, IP)
+        np.testing.assert_array_equal(I, Io)
+
+
+def test_torch_cuda_tensors_roundtrip():
+    import torch
+    trx = _engine()
+    xb, xq = util.gaussian(20000, 256, 81), util.gaussian(130, 256, 82)
+    idx = trx.IndexFlatIP(256)
+    idx.add(torch.from_numpy(xb).cuda())
+    D, I = idx.search(torch.from_numpy(xq).cuda(), 10)
+    assert D.is_cuda and I.is_cuda and I.dtype == torch.int64
+    oracle.check_parity(D.cpu().numpy(), I.cpu().numpy(), xb, xq, 10, IP)
+    idx.close()
+
+
+def test_merge_topk_equals_unsharded():
+    import torch
+    trx = _engine()
+    n, d, nq, k, G = 48000, 128, 50, 10, 4
+    xb, xq = util.gaussian(n, d, 91), util.gaussian(nq, d, 92)
+    Ds, Is = [], []
+    for g in range(G):
+        lo, hi = g * n // G, (g + 1) * n // G
+        idx = trx.IndexFlatIP(d)
+        idx.add(xb[lo:hi]); idx.set_id_offset(lo)
+        Dg, Ig = idx.search(torch.from_numpy(xq).cuda(), k)
+        Ds.append(Dg); Is.append(Ig); idx.close()
+    D, I = trx.merge_topk(torch.stack(Ds), torch.stack(Is), IP)
+    oracle.check_parity(D.cpu().numpy(), I.cpu().numpy(), xb, xq, k, IP)

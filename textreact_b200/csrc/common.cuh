@@ -1,0 +1,143 @@
+// common.cuh -- shared declarations for libtrx.so (B200 / sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/trx.h"
+
+namespace trx {
+
+void set_error(const char* fmt, ...);
+
+#define TRX_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            ::trx::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (e_ == cudaErrorMemoryAllocation) ? TRX_ENOMEM : TRX_ECUDA;              \
+        }                                                                                   \
+    } while (0)
+
+#define TRX_TRY(call)              \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != TRX_OK) return rc_; \
+    } while (0)
+
+// Monotone float -> uint32: a > b  <=>  f2key(a) > f2key(b)  (-0 < +0, NaNs at the ends).
+__host__ __device__ __forceinline__ uint32_t f2key(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key2f(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+// 64-bit sort key: ascending order == (score descending, id ascending).
+__host__ __device__ __forceinline__ uint64_t pack_key(float score, uint32_t id) {
+    return ((uint64_t)(~f2key(score)) << 32) | (uint64_t)id;
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return key2f(~(uint32_t)(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return (uint32_t)k; }
+static constexpr uint64_t KEY_SENTINEL = 0xffffffffffffffffull;  // sorts last
+
+// A prefilter candidate: bf16-pipeline score + local row.
+struct __align__(8) Cand {
+    float score;
+    int32_t row;
+};
+
+constexpr int kSampleRank = 16;  // threshold = this rank of the sample's scores
+
+// ---- host launchers (each returns TRX_*) ---------------------------------------------------
+
+// K1: fp32 rows -> bf16 rows (pitch Kp, zero padded; L2: |x|^2 split in 3 bf16 at cols d..d+2),
+// squared norms, running max of the squared norm (as float bits).
+int launch_ingest(const float* x, int64_t n, int d, int Kp, int metric, __nv_bfloat16* x16,
+                  float* xnorm2, uint32_t* norm2_max_bits, cudaStream_t st);
+// One pseudo-randomly chosen row out of every `rate` consecutive rows -> xs16 [ns, Kp].
+int launch_sample_gather(const __nv_bfloat16* x16, int64_t n, int Kp, int rate, __nv_bfloat16* xs16,
+                         int64_t ns, cudaStream_t st);
+// Queries: fp32 [B,d] -> bf16 [B,Kp] (L2: 2q and -1,-1,-1 in the norm columns) + |q|^2.
+int launch_query_prep(const float* q, int64_t B, int d, int Kp, int metric, __nv_bfloat16* q16,
+                      float* qnorm2, cudaStream_t st);
+
+// K3: CUDA-core streaming scorer.
+//   fp32 mode : exact scores (IP: q.x ; L2: -sum (q-x)^2), rows masked by group get -inf.
+//   bf16 mode : prefilter scores over the Kp-wide augmented rows (same formula as K2).
+// scores mode writes out[q*out_ld + row]; append mode emits candidates with score > thr[q].
+struct StreamArgs {
+    const void* x; int64_t pitch; int64_t n; int d;   // d = number of columns to reduce over
+    const float* q32; const __nv_bfloat16* q16; int64_t q_pitch; int64_t nq;
+    const int32_t* groups; const int32_t* excl;
+    float* out; int64_t out_ld;                       // scores mode
+    const float* thr; Cand* cand; uint32_t* cand_cnt; int cap;  // append mode
+    int metric; bool bf16; bool append;
+};
+int launch_stream(const StreamArgs& a, int sm_count, cudaStream_t st);
+
+// r-th largest value of each row of s[nq][ld] (first n entries) -> thr[nq]; rows with fewer
+// than r finite entries get -inf.
+int launch_row_kth(const float* s, int64_t ld, int64_t n, int64_t nq, int r, float* thr,
+                   cudaStream_t st);
+
+// Exact top-k of materialised scores s[nq][ld] ("larger is better", -inf = ineligible):
+// (score desc, id asc), padded with id -1.  negate_out: D = -score (L2).  qmap (nullable):
+// output row of query i is qmap[i].
+int launch_exact_topk(const float* s, int64_t ld, int64_t n, int64_t nq, int k, bool negate_out,
+                      int64_t id_offset, const int32_t* qmap, float* D, int64_t* I, cudaStream_t st);
+
+// K4: candidates -> exact fp32 rescore -> certificate -> final top-k.
+struct RescoreArgs {
+    const Cand* cand; const uint32_t* cand_cnt; int cap;
+    const float* thr;          // prefilter threshold per query (-inf: every row is a candidate)
+    const float* eps;          // certificate slack per query (score units)
+    const float* x32; int d; int64_t n;
+    const float* q32; int64_t nq;
+    const int32_t* groups; const int32_t* excl;
+    int k; int metric; int64_t id_offset;
+    float* D; int64_t* I;
+    int32_t* fb_list; uint32_t* fb_count;  // queries that need the exact scan
+    uint64_t* counters;                     // [0] rescored rows [1] uncertified [2] overflow [3] candidates
+};
+int launch_rescore(const RescoreArgs& a, cudaStream_t st);
+
+// certificate slack: eps[q] = c * |q| * max|x| (IP) ; L2 doubles it and adds norm slack.
+int launch_eps(const float* qnorm2, const uint32_t* norm2_max_bits, int64_t nq, int d, int metric,
+               float* eps, cudaStream_t st);
+
+// K2: tcgen05 scoring GEMM.  A = queries bf16 [nq, Kp], B = rows bf16 [n, Kp].
+struct UmmaArgs {
+    const __nv_bfloat16* q16; int64_t nq;
+    const __nv_bfloat16* x16; int64_t n; int Kp;
+    // mode 0: store fp32 scores out[q*out_ld + row]; mode 1: append candidates > thr[q];
+    // mode 2: slot maxima -> out[(q*S + slice)*32 + slot]
+    int mode;
+    float* out; int64_t out_ld;
+    const float* thr; Cand* cand; uint32_t* cand_cnt; int cap;
+};
+int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st);
+int umma_init();  // resolves cuTensorMapEncodeTiled
+int umma_num_slices(int64_t n);  // S of the SLOTMAX mode (out = slots[nq][S][32])
+// r-th largest of the S*32 slot maxima of each query -> thr
+int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st);
+
+// K5: merge G sorted lists per query.
+int launch_merge(int metric, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, float* D,
+                 int64_t* I, cudaStream_t st);
+
+void count_launch(int n = 1);
+
+}  // namespace trx

@@ -1,0 +1,182 @@
+// k1_ingest.cu -- corpus / query ingestion kernels (HBM-bound, one warp per row).
+//
+// Replaces the storage half of faiss `index.add(train_fps)` (retrieve/retrieve_faiss.py:66):
+// FAISS keeps one fp32 row-major copy; we keep that copy (for the exact rescore) plus a bf16
+// copy laid out for TMA (row pitch Kp, a multiple of 64 elements = one 128-byte swizzle row).
+#include "common.cuh"
+
+namespace trx {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Split a non-negative fp32 value into three bf16 whose sum reproduces it to ~2^-24.
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+    a = __float2bfloat16_rn(v);
+    float r1 = v - __bfloat162float(a);
+    b = __float2bfloat16_rn(r1);
+    float r2 = r1 - __bfloat162float(b);
+    c = __float2bfloat16_rn(r2);
+}
+
+// grid-stride over rows, one warp per row.
+__global__ void __launch_bounds__(256) k1_ingest_kernel(const float* __restrict__ x, int64_t n, int d, int Kp,
+                                                        int metric, __nv_bfloat16* __restrict__ x16,
+                                                        float* __restrict__ xnorm2,
+                                                        uint32_t* __restrict__ norm2_max_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float wmax = 0.f;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const float* xr = x + r * (int64_t)d;
+        __nv_bfloat16* yr = x16 + r * (int64_t)Kp;
+        float acc = 0.f;
+        if ((d & 3) == 0) {
+            const float4* x4 = reinterpret_cast<const float4*>(xr);
+            for (int c = lane; c < (d >> 2); c += 32) {
+                float4 v = __ldg(x4 + c);
+                acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc);
+                acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(yr + 4 * c) = pk;
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) {
+                float v = __ldg(xr + c);
+                acc = fmaf(v, v, acc);
+                yr[c] = __float2bfloat16_rn(v);
+            }
+        }
+        acc = warp_sum(acc);
+        // padding columns (and the norm split for L2)
+        for (int c = d + lane; c < Kp; c += 32) yr[c] = __float2bfloat16_rn(0.f);
+        __syncwarp();
+        if (lane == 0) {
+            xnorm2[r] = acc;
+            if (metric == TRX_METRIC_L2) {
+                __nv_bfloat16 a, b, c3;
+                split3(acc, a, b, c3);
+                yr[d] = a; yr[d + 1] = b; yr[d + 2] = c3;
+            }
+            wmax = fmaxf(wmax, acc);
+        }
+    }
+    if (lane == 0 && wmax > 0.f) atomicMax(norm2_max_bits, __float_as_uint(wmax));  // >= 0: bit order == value order
+}
+
+int launch_ingest(const float* x, int64_t n, int d, int Kp, int metric, __nv_bfloat16* x16, float* xnorm2,
+                  uint32_t* norm2_max_bits, cudaStream_t st) {
+    if (n <= 0) return TRX_OK;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k1_ingest_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, d, Kp, metric, x16, xnorm2, norm2_max_bits);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+// Sample row j of group g = rows [g*rate, (g+1)*rate): a hash picks the member, so that periodic
+// structure in the add order cannot alias with the sampling stride.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) k1_sample_gather_kernel(const __nv_bfloat16* __restrict__ x16, int64_t n,
+                                                               int Kp, int rate,
+                                                               __nv_bfloat16* __restrict__ xs16, int64_t ns) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int vec = Kp >> 3;  // 16-byte chunks per row (Kp % 64 == 0)
+    for (int64_t g = warp0; g < ns; g += nwarps) {
+        int64_t base = g * rate;
+        int64_t span = n - base < rate ? n - base : rate;
+        int64_t src = base + (int64_t)(mix32((uint32_t)g * 2654435761u + 12345u) % (uint32_t)span);
+        const uint4* s4 = reinterpret_cast<const uint4*>(x16 + src * (int64_t)Kp);
+        uint4* d4 = reinterpret_cast<uint4*>(xs16 + g * (int64_t)Kp);
+        for (int c = lane; c < vec; c += 32) d4[c] = __ldg(s4 + c);
+    }
+}
+
+int launch_sample_gather(const __nv_bfloat16* x16, int64_t n, int Kp, int rate, __nv_bfloat16* xs16, int64_t ns,
+                         cudaStream_t st) {
+    if (ns <= 0) return TRX_OK;
+    int64_t blocks = (ns + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k1_sample_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(x16, n, Kp, rate, xs16, ns);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+__global__ void __launch_bounds__(256) k1_query_prep_kernel(const float* __restrict__ q, int64_t B, int d, int Kp,
+                                                            int metric, __nv_bfloat16* __restrict__ q16,
+                                                            float* __restrict__ qnorm2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float scale = metric == TRX_METRIC_L2 ? 2.f : 1.f;  // exact in bf16
+    for (int64_t r = warp0; r < B; r += nwarps) {
+        const float* qr = q + r * (int64_t)d;
+        __nv_bfloat16* yr = q16 + r * (int64_t)Kp;
+        float acc = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            float v = __ldg(qr + c);
+            acc = fmaf(v, v, acc);
+            yr[c] = __float2bfloat16_rn(scale * __bfloat162float(__float2bfloat16_rn(v)));
+        }
+        for (int c = d + lane; c < Kp; c += 32)
+            yr[c] = __float2bfloat16_rn((metric == TRX_METRIC_L2 && c < d + 3) ? -1.f : 0.f);
+        acc = warp_sum(acc);
+        if (lane == 0) qnorm2[r] = acc;
+    }
+}
+
+int launch_query_prep(const float* q, int64_t B, int d, int Kp, int metric, __nv_bfloat16* q16, float* qnorm2,
+                      cudaStream_t st) {
+    if (B <= 0) return TRX_OK;
+    int64_t blocks = (B + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k1_query_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, B, d, Kp, metric, q16, qnorm2);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+// Certificate slack (see DESIGN.md "exactness certificate").
+//   bf16 rounding: |q^.x^ - q.x| <= (2u + u^2) sum|q_i x_i| <= (2u+u^2) |q||x|, u = 2^-9
+//   fp32 accumulation (tensor core, prefilter) and fp32 rescore: each <= d * 2^-23 |q||x| (loose)
+//   IP : eps = (2^-8 * 1.002 + 2 d 2^-23) |q| max|x|
+//   L2 : prefilter score is 2 q.x - |x|^2  ->  2x the IP slack, + 2^-22 max|x|^2 for the 3-way norm
+//        split and + 2^-21 (|q|^2 + max|x|^2) for the fp32 evaluation of |q|^2 - sum (q-x)^2.
+__global__ void k1_eps_kernel(const float* __restrict__ qnorm2, const uint32_t* __restrict__ norm2_max_bits,
+                              int64_t nq, int d, int metric, float* __restrict__ eps) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float xm2 = __uint_as_float(*norm2_max_bits);
+    float qn = sqrtf(qnorm2[i]) * 1.000001f, xn = sqrtf(xm2) * 1.000001f;
+    float c = 0.00390625f * 1.002f + 2.f * (float)(d + 3) * 1.1920929e-7f;
+    float e = c * qn * xn;
+    if (metric == TRX_METRIC_L2) e = 2.f * e + 2.4e-7f * xm2 + 4.8e-7f * (qnorm2[i] + xm2);
+    eps[i] = e * 1.0001f + 1e-37f;
+}
+
+int launch_eps(const float* qnorm2, const uint32_t* norm2_max_bits, int64_t nq, int d, int metric, float* eps,
+               cudaStream_t st) {
+    if (nq <= 0) return TRX_OK;
+    k1_eps_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(qnorm2, norm2_max_bits, nq, d, metric, eps);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+}  // namespace trx

@@ -1,0 +1,376 @@
+// k2_score_umma.cu -- the batched scoring kernel: TMA-fed tcgen05.mma tiles over the bf16 corpus,
+// fp32 accumulators in TMEM, per-query selection fused into the epilogue so the score matrix
+// never reaches HBM.
+//
+// Replaces the `sgemm` + heap/reservoir inner loop of faiss `index.search`
+// (retrieve/retrieve_faiss.py:71) for batched queries.
+//
+//   D[128 queries x 256 corpus rows] (TMEM, fp32) += A[128 x 64] (smem, bf16) . B[256 x 64]^T
+//
+// Roles (one CTA per SM, 256 threads):
+//   warp 0    TMA producer: cp.async.bulk.tensor into a 4-stage 128B-swizzled smem ring
+//   warp 1    MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16)
+//   warp 2    TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32, one query row per thread
+// Epilogue modes:
+//   STORE    fp32 scores to HBM (tests / profiling only)
+//   THRESH   compare against the per-query threshold, append (score,row) candidates (rare path)
+//   SLOTMAX  running max of every (column mod 32) slot -> threshold estimation on the sample
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace trx {
+
+namespace {
+
+constexpr int BM = 128;      // queries per tile   (UMMA M)
+constexpr int BN = 256;      // corpus rows per tile (UMMA N)
+constexpr int BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 256;
+
+enum { MODE_STORE = 0, MODE_THRESH = 1, MODE_SLOTMAX = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms, SBO = 1024 B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);  // start address
+    d |= (uint64_t)1 << 16;                   // LBO (unused for swizzled K-major; CUTLASS writes 1)
+    d |= (uint64_t)(1024 >> 4) << 32;         // SBO
+    d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct KParams {
+    int64_t nq, n;
+    int KB;          // k-blocks
+    int MT, NT, S;   // query tiles, row tiles, slices (S == NT for STORE/THRESH)
+    float* out; int64_t out_ld;
+    const float* thr; Cand* cand; uint32_t* cand_cnt; int cap;
+    float* slots;    // SLOTMAX: [nq][S][32]
+};
+
+}  // namespace
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, KParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    // barrier layout (8 bytes each): full[STAGES] empty[STAGES] tfull[2] tempty[2] ; then tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_units = p.MT * p.S;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                const int mt = u % p.MT, sl = u / p.MT;
+                const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
+                for (int nt = nt0; nt < nt1; nt++) {
+                    for (int kb = 0; kb < p.KB; kb++) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                        tma_load_2d(sa, &tmap_q, full_bar(stage), kb * BK, mt * BM);
+                        tma_load_2d(sa + A_BYTES, &tmap_x, full_bar(stage), kb * BK, nt * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0; uint32_t phase = 0;
+        int as = 0; uint32_t aphase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int sl = u / p.MT;
+            const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
+            for (int nt = nt0; nt < nt1; nt++) {
+                mbar_wait(tempty_bar(as), aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < p.KB; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                        const uint64_t adesc = make_smem_desc(sa);
+                        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++) {
+                            // advance 16 elements = 32 bytes inside the 128-byte swizzle row
+                            tc_mma(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                   (kb | k) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(empty_bar(stage));                      // frees the smem slot when the MMAs retire
+                        if (kb == p.KB - 1) tc_commit(tfull_bar(as));     // accumulator ready
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int wq = warp & 3;  // TMEM lane quarter this warp may access
+        int as = 0; uint32_t aphase = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            const int mt = u % p.MT, sl = u / p.MT;
+            const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
+            const int64_t row = (int64_t)mt * BM + wq * 32 + lane;  // query handled by this thread
+            const bool row_ok = row < p.nq;
+            float thr = INFINITY;
+            if (MODE == MODE_THRESH && row_ok) thr = p.thr[row];
+            float slot[32];
+            if (MODE == MODE_SLOTMAX) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) slot[j] = -INFINITY;
+            }
+            for (int nt = nt0; nt < nt1; nt++) {
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+                const int64_t col0 = (int64_t)nt * BN;
+                const bool full_tile = col0 + BN <= p.n;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch++) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
+                    tc_wait_ld();
+                    const int64_t cbase = col0 + ch * 32;
+                    if (MODE == MODE_STORE) {
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (cbase + j < p.n) p.out[row * p.out_ld + cbase + j] = __uint_as_float(v[j]);
+                        }
+                    } else if (MODE == MODE_THRESH) {
+                        float mx = __uint_as_float(v[0]);
+#pragma unroll
+                        for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        if (mx > thr) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                float s = __uint_as_float(v[j]);
+                                if (s > thr && cbase + j < p.n) {
+                                    uint32_t pos = atomicAdd(p.cand_cnt + row, 1u);
+                                    if (pos < (uint32_t)p.cap) {
+                                        Cand c; c.score = s; c.row = (int32_t)(cbase + j);
+                                        p.cand[row * (int64_t)p.cap + pos] = c;
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        if (full_tile) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) slot[j] = fmaxf(slot[j], __uint_as_float(v[j]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (cbase + j < p.n) slot[j] = fmaxf(slot[j], __uint_as_float(v[j]));
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(as));
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+            if (MODE == MODE_SLOTMAX && row_ok) {
+                float* dst = p.slots + (row * p.S + sl) * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(slot[j], slot[j + 1], slot[j + 2], slot[j + 3]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d (rows=%lld Kp=%d)", (int)r, (long long)rows, Kp); return TRX_ECUDA; }
+    return TRX_OK;
+}
+
+template <int MODE>
+int launch_mode(const CUtensorMap& mq, const CUtensorMap& mx, const KParams& p, int grid, cudaStream_t st) {
+    auto kern = k2_umma_kernel<MODE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_done = true;
+    }
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mx, p);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+}  // namespace
+
+int umma_init() {
+    if (g_encode) return TRX_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    TRX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) { set_error("cuTensorMapEncodeTiled not available"); return TRX_ECUDA; }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return TRX_OK;
+}
+
+int umma_num_slices(int64_t n) {
+    int64_t NT = (n + BN - 1) / BN;
+    return (int)(NT < 8 ? NT : 8);
+}
+
+int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st) {
+    if (a.nq <= 0 || a.n <= 0) return TRX_OK;
+    TRX_TRY(umma_init());
+    if (a.Kp % BK) { set_error("k2: Kp=%d not a multiple of %d", a.Kp, BK); return TRX_EINVAL; }
+    CUtensorMap mq, mx;
+    TRX_TRY(make_map(&mq, a.q16, a.nq, a.Kp, BM));
+    TRX_TRY(make_map(&mx, a.x16, a.n, a.Kp, BN));
+    KParams p;
+    p.nq = a.nq; p.n = a.n; p.KB = a.Kp / BK;
+    p.MT = (int)((a.nq + BM - 1) / BM);
+    p.NT = (int)((a.n + BN - 1) / BN);
+    p.S = a.mode == MODE_SLOTMAX ? umma_num_slices(a.n) : p.NT;
+    p.out = a.out; p.out_ld = a.out_ld;
+    p.thr = a.thr; p.cand = a.cand; p.cand_cnt = a.cand_cnt; p.cap = a.cap;
+    p.slots = a.out;  // SLOTMAX reuses `out` as the [nq][S][32] slot buffer
+    int64_t units = (int64_t)p.MT * p.S;
+    int grid = (int)(units < sm_count ? units : sm_count);
+    switch (a.mode) {
+        case MODE_STORE: return launch_mode<MODE_STORE>(mq, mx, p, grid, st);
+        case MODE_THRESH: return launch_mode<MODE_THRESH>(mq, mx, p, grid, st);
+        case MODE_SLOTMAX: return launch_mode<MODE_SLOTMAX>(mq, mx, p, grid, st);
+    }
+    set_error("k2: bad mode %d", a.mode);
+    return TRX_EINVAL;
+}
+
+}  // namespace trx

@@ -1,0 +1,479 @@
+// k4_select.cu -- selection kernels: threshold estimation, exact fp32 rescore + certificate,
+// exact radix top-k over materialised scores, and the k-way shard merge.
+//
+// Together with the scorers (k2/k3) these replace the "heap / reservoir" half of faiss
+// `index.search` (retrieve/retrieve_faiss.py:71).  Ordering everywhere: score descending
+// ("larger is better": IP score, or minus squared distance for L2), ties by ascending id --
+// the (val, id) comparison of FAISS heaps.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace trx {
+
+// ---------------------------------------------------------------------------------------------
+// block-wide helpers
+// ---------------------------------------------------------------------------------------------
+
+// In-place ascending bitonic sort of P (power of two) 64-bit keys in shared memory.
+__device__ __forceinline__ void bitonic_sort_u64(uint64_t* keys, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                uint64_t a = keys[i], b = keys[j];
+                bool up = (i & size) == 0;
+                if ((a > b) == up) { keys[i] = b; keys[j] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// r-th largest (1-based) key among s[0..n) by 4 x 8-bit MSB-first radix passes.
+// hist: 256 x uint32 shared; bc: 4 x uint32 shared.  Returns through shared broadcast.
+// cnt_gt = number of elements with key strictly greater than the result.
+__device__ void block_radix_select(const float* __restrict__ s, int64_t n, uint32_t r, uint32_t* hist,
+                                   uint32_t* bc, uint32_t& kth_key, uint32_t& cnt_gt) {
+    uint32_t prefix = 0, mask = 0, remaining = r, gt = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t key = f2key(s[i]);
+            bool in = (key & mask) == prefix;
+            uint32_t bin = (key >> shift) & 255u;
+            // warp-aggregate same-bin increments (scores cluster in a handful of exponent bins)
+            uint32_t act = __ballot_sync(__activemask(), in);
+            if (in) {
+                uint32_t peers = __match_any_sync(act, bin);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cum = 0;
+            int b = 255;
+            for (; b > 0; b--) {
+                uint32_t c = hist[b];
+                if (cum + c >= remaining) break;
+                cum += c;
+            }
+            bc[0] = (uint32_t)b;
+            bc[1] = cum;
+        }
+        __syncthreads();
+        prefix |= bc[0] << shift;
+        mask |= 255u << shift;
+        remaining -= bc[1];
+        gt += bc[1];
+        __syncthreads();
+    }
+    kth_key = prefix;
+    cnt_gt = gt;
+}
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* scratch /*>=33*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = threadIdx.x < (blockDim.x >> 5) ? scratch[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (threadIdx.x == 0) scratch[32] = w;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// ---------------------------------------------------------------------------------------------
+// row_kth: threshold = r-th largest of a materialised score row (K3 sample pass)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) row_kth_kernel(const float* __restrict__ s, int64_t ld, int64_t n, int r,
+                                                      float* __restrict__ thr) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t bc[4];
+    __shared__ uint32_t scratch[33];
+    const float* row = s + (int64_t)blockIdx.x * ld;
+    uint32_t fin = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) fin += row[i] > -INFINITY ? 1u : 0u;
+    fin = block_sum_u32(fin, scratch);
+    if (fin < (uint32_t)r) {
+        if (threadIdx.x == 0) thr[blockIdx.x] = -INFINITY;
+        return;
+    }
+    uint32_t key, gt;
+    block_radix_select(row, n, (uint32_t)r, hist, bc, key, gt);
+    if (threadIdx.x == 0) thr[blockIdx.x] = key2f(key);
+}
+
+int launch_row_kth(const float* s, int64_t ld, int64_t n, int64_t nq, int r, float* thr, cudaStream_t st) {
+    if (nq <= 0) return TRX_OK;
+    row_kth_kernel<<<(unsigned)nq, 512, 0, st>>>(s, ld, n, r, thr);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact top-k over materialised scores (certified fallback / forced exact path)
+// ---------------------------------------------------------------------------------------------
+constexpr int kExactMaxK = 2048;
+
+__global__ void __launch_bounds__(1024) exact_topk_kernel(const float* __restrict__ s, int64_t ld, int64_t n, int k,
+                                                          bool negate_out, int64_t id_offset,
+                                                          const int32_t* __restrict__ qmap, float* __restrict__ D,
+                                                          int64_t* __restrict__ I) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t bc[4];
+    __shared__ uint32_t scratch[33];
+    __shared__ uint32_t warp_eq[32];
+    __shared__ uint32_t out_ctr;
+    __shared__ uint64_t okeys[kExactMaxK];
+
+    const float* row = s + (int64_t)blockIdx.x * ld;
+    const int64_t orow = qmap ? (int64_t)qmap[blockIdx.x] : (int64_t)blockIdx.x;
+    float* Dq = D + orow * k;
+    int64_t* Iq = I + orow * k;
+    const float fill = negate_out ? FLT_MAX : -FLT_MAX;
+
+    uint32_t elig = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) elig += row[i] > -INFINITY ? 1u : 0u;
+    elig = block_sum_u32(elig, scratch);
+    const uint32_t r = elig < (uint32_t)k ? elig : (uint32_t)k;
+    const int P = next_pow2(k);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) okeys[i] = KEY_SENTINEL;
+    if (threadIdx.x == 0) out_ctr = 0;
+    __syncthreads();
+    if (r > 0) {
+        uint32_t kth, gt;
+        block_radix_select(row, n, r, hist, bc, kth, gt);
+        const uint32_t need_eq = r - gt;
+        uint32_t eq_base = 0;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int64_t t0 = 0; t0 < n; t0 += blockDim.x) {
+            int64_t i = t0 + threadIdx.x;
+            float v = i < n ? row[i] : -INFINITY;
+            uint32_t key = f2key(v);
+            bool is_gt = i < n && key > kth;
+            bool is_eq = i < n && key == kth && v > -INFINITY;
+            if (is_gt) {
+                uint32_t pos = atomicAdd(&out_ctr, 1u);
+                okeys[pos] = pack_key(v, (uint32_t)i);
+            }
+            if (eq_base < need_eq) {  // uniform across the block
+                uint32_t b = __ballot_sync(0xffffffffu, is_eq);
+                if (lane == 0) warp_eq[wid] = __popc(b);
+                __syncthreads();
+                uint32_t before = 0, total = 0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+                    uint32_t c = warp_eq[w];
+                    if (w < wid) before += c;
+                    total += c;
+                }
+                uint32_t rank = eq_base + before + __popc(b & ((1u << lane) - 1u));
+                if (is_eq && rank < need_eq) {
+                    uint32_t pos = atomicAdd(&out_ctr, 1u);
+                    okeys[pos] = pack_key(v, (uint32_t)i);
+                }
+                eq_base += total;
+                __syncthreads();
+            }
+        }
+    }
+    bitonic_sort_u64(okeys, P);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        uint64_t key = okeys[j];
+        if (key == KEY_SENTINEL || j >= (int)r) { Dq[j] = fill; Iq[j] = -1; }
+        else {
+            float sc = key_score(key);
+            Dq[j] = negate_out ? -sc : sc;
+            Iq[j] = (int64_t)key_id(key) + id_offset;
+        }
+    }
+}
+
+int launch_exact_topk(const float* s, int64_t ld, int64_t n, int64_t nq, int k, bool negate_out,
+                      int64_t id_offset, const int32_t* qmap, float* D, int64_t* I, cudaStream_t st) {
+    if (nq <= 0) return TRX_OK;
+    if (k > kExactMaxK) { set_error("k=%d exceeds the supported maximum %d", k, kExactMaxK); return TRX_EINVAL; }
+    exact_topk_kernel<<<(unsigned)nq, 1024, 0, st>>>(s, ld, n, k, negate_out, id_offset, qmap, D, I);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: candidates -> exact fp32 rescore -> certificate -> final top-k
+// ---------------------------------------------------------------------------------------------
+// One CTA (256 threads) per query.  Candidates come from a bf16 prefilter whose invariant is:
+// every row NOT in the list has prefilter score <= thr[q].  Let eps bound |prefilter - exact|.
+// After rescoring the best m candidates (by prefilter score) exactly, the exact top-k of those m
+// is the exact top-k of the whole corpus if  exact_k > max(next prefilter score, thr) + eps.
+// Otherwise rescore more; if the list is exhausted the query goes to the exact scan.
+template <int METRIC>
+__device__ __forceinline__ float exact_score_warp(const float* __restrict__ xr, const float* __restrict__ sq, int d,
+                                                  int lane) {
+    float acc = 0.f;
+    if ((d & 3) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        const float4* q4 = reinterpret_cast<const float4*>(sq);
+        for (int c = lane; c < (d >> 2); c += 32) {
+            float4 x = __ldg(x4 + c);
+            float4 q = q4[c];
+            if (METRIC == TRX_METRIC_INNER_PRODUCT) {
+                acc = fmaf(x.x, q.x, acc); acc = fmaf(x.y, q.y, acc);
+                acc = fmaf(x.z, q.z, acc); acc = fmaf(x.w, q.w, acc);
+            } else {
+                float t0 = q.x - x.x, t1 = q.y - x.y, t2 = q.z - x.z, t3 = q.w - x.w;
+                acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc);
+                acc = fmaf(t2, t2, acc); acc = fmaf(t3, t3, acc);
+            }
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) {
+            float x = __ldg(xr + c), q = sq[c];
+            if (METRIC == TRX_METRIC_INNER_PRODUCT) acc = fmaf(x, q, acc);
+            else { float t = q - x; acc = fmaf(t, t, acc); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return METRIC == TRX_METRIC_INNER_PRODUCT ? acc : -acc;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(256) k4_rescore_kernel(RescoreArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: keys[cap] u64 | ekeys[cap] u64 | q[d] f32
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* ekeys = keys + a.cap;
+    float* sq = reinterpret_cast<float*>(ekeys + a.cap);
+    __shared__ uint32_t s_valid;
+    __shared__ float s_qn2;
+
+    const int64_t q = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int k = a.k;
+    float* Dq = a.D + q * k;
+    int64_t* Iq = a.I + q * k;
+    const float fill = METRIC == TRX_METRIC_L2 ? FLT_MAX : -FLT_MAX;
+
+    const uint32_t cnt_raw = a.cand_cnt[q];
+    if (cnt_raw > (uint32_t)a.cap) {  // list overflowed: invariant lost
+        if (threadIdx.x == 0) {
+            a.fb_list[atomicAdd(a.fb_count, 1u)] = (int32_t)q;
+            atomicAdd((unsigned long long*)&a.counters[2], 1ull);
+            atomicAdd((unsigned long long*)&a.counters[3], (unsigned long long)cnt_raw);
+        }
+        return;
+    }
+    const int n_c = (int)cnt_raw;
+    const int32_t ex = (a.excl != nullptr && a.groups != nullptr) ? a.excl[q] : -1;
+    if (threadIdx.x == 0) { s_valid = 0; s_qn2 = 0.f; }
+    float qn2_part = 0.f;
+    for (int c = threadIdx.x; c < a.d; c += blockDim.x) {
+        float v = a.q32[q * (int64_t)a.d + c];
+        sq[c] = v;
+        qn2_part = fmaf(v, v, qn2_part);
+    }
+    const int P = next_pow2(n_c);
+    __syncthreads();
+    uint32_t my_valid = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t key = KEY_SENTINEL;
+        if (i < n_c) {
+            Cand c = a.cand[q * (int64_t)a.cap + i];
+            bool ok = !(ex >= 0 && __ldg(a.groups + c.row) == ex);
+            if (ok) { key = pack_key(c.score, (uint32_t)c.row); my_valid++; }
+        }
+        keys[i] = key;
+    }
+    if (my_valid) atomicAdd(&s_valid, my_valid);
+    if (METRIC == TRX_METRIC_L2) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qn2_part += __shfl_xor_sync(0xffffffffu, qn2_part, o);
+        if (lane == 0) atomicAdd(&s_qn2, qn2_part);
+    }
+    bitonic_sort_u64(keys, P);  // (prefilter score desc, row asc); masked / padding last
+    const int n_valid = (int)s_valid;
+    const float qn2 = s_qn2;
+    const float thr = a.thr[q];
+    const float eps = a.eps[q];
+    const bool complete = !(thr > -INFINITY);  // every eligible row is in the list
+
+    int m_done = 0;
+    int m = k + (k / 4 > 16 ? k / 4 : 16);
+    m = (m + 7) & ~7;
+    if (m > n_valid) m = n_valid;
+    bool certified = false;
+    for (;;) {
+        for (int i = m_done + wid; i < m; i += nwarp) {
+            uint32_t row = key_id(keys[i]);
+            float e = exact_score_warp<METRIC>(a.x32 + (int64_t)row * a.d, sq, a.d, lane);
+            if (lane == 0) ekeys[i] = pack_key(e, row);
+        }
+        const int P2 = next_pow2(m);
+        for (int i = m + threadIdx.x; i < P2; i += blockDim.x) ekeys[i] = KEY_SENTINEL;
+        bitonic_sort_u64(ekeys, P2);  // includes the leading barrier
+        if (m == n_valid && complete) certified = true;
+        else if (m >= k) {
+            float sk = key_score(ekeys[k - 1]);
+            if (METRIC == TRX_METRIC_L2) sk += qn2;  // prefilter domain: |q|^2 - dist
+            float bound = m < n_valid ? key_score(keys[m]) : thr;
+            certified = sk > bound + eps;
+        }
+        if (certified || m == n_valid) break;
+        m_done = m;
+        m = 2 * m < n_valid ? 2 * m : n_valid;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)m);
+        atomicAdd((unsigned long long*)&a.counters[3], (unsigned long long)n_c);
+    }
+    if (!certified) {
+        if (threadIdx.x == 0) {
+            a.fb_list[atomicAdd(a.fb_count, 1u)] = (int32_t)q;
+            atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+        }
+        return;
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        if (j < m) {
+            uint64_t key = ekeys[j];
+            float sc = key_score(key);
+            Dq[j] = METRIC == TRX_METRIC_L2 ? -sc : sc;
+            Iq[j] = (int64_t)key_id(key) + a.id_offset;
+        } else { Dq[j] = fill; Iq[j] = -1; }
+    }
+}
+
+int launch_rescore(const RescoreArgs& a, cudaStream_t st) {
+    if (a.nq <= 0) return TRX_OK;
+    size_t smem = (size_t)a.cap * 16 + (size_t)a.d * 4;
+    if (smem > 200 * 1024) { set_error("k4: cap=%d d=%d exceed shared memory", a.cap, a.d); return TRX_EINVAL; }
+    if (a.metric == TRX_METRIC_L2) {
+        auto kern = k4_rescore_kernel<TRX_METRIC_L2>;
+        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)a.nq, 256, smem, st>>>(a);
+    } else {
+        auto kern = k4_rescore_kernel<TRX_METRIC_INNER_PRODUCT>;
+        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)a.nq, 256, smem, st>>>(a);
+    }
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: k-way merge of G per-shard sorted lists (after the NCCL all-gather)
+// ---------------------------------------------------------------------------------------------
+// Position index g*k+j is the tie-break: shards hold ascending, disjoint id ranges and every
+// list is already (score, id)-ordered, so position order == id order among equal scores.
+__global__ void __launch_bounds__(256) k5_merge_kernel(int metric, const float* __restrict__ Dg,
+                                                       const int64_t* __restrict__ Ig, int G, int64_t nq, int k,
+                                                       float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    const int64_t q = blockIdx.x;
+    const int total = G * k;
+    const int P = next_pow2(total);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t key = KEY_SENTINEL;
+        if (i < total) {
+            int g = i / k, j = i - g * k;
+            int64_t src = ((int64_t)g * nq + q) * k + j;
+            if (Ig[src] >= 0) {
+                float v = Dg[src];
+                key = pack_key(metric == TRX_METRIC_L2 ? -v : v, (uint32_t)i);
+            }
+        }
+        keys[i] = key;
+    }
+    bitonic_sort_u64(keys, P);
+    const float fill = metric == TRX_METRIC_L2 ? FLT_MAX : -FLT_MAX;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        uint64_t key = keys[j];
+        if (key == KEY_SENTINEL) { D[q * k + j] = fill; I[q * k + j] = -1; }
+        else {
+            int pos = (int)key_id(key);
+            int g = pos / k, jj = pos - g * k;
+            int64_t src = ((int64_t)g * nq + q) * k + jj;
+            D[q * k + j] = Dg[src];
+            I[q * k + j] = Ig[src];
+        }
+    }
+}
+
+int launch_merge(int metric, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, float* D, int64_t* I,
+                 cudaStream_t st) {
+    if (nq <= 0) return TRX_OK;
+    int64_t total = (int64_t)G * k;
+    int P = 2;
+    while (P < total) P <<= 1;
+    size_t smem = (size_t)P * 8;
+    if (smem > 200 * 1024) { set_error("merge: G*k=%lld too large", (long long)total); return TRX_EINVAL; }
+    TRX_CUDA(cudaFuncSetAttribute(k5_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(metric, Dg, Ig, G, nq, k, D, I);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// slot_thr: threshold from the K2 SLOTMAX epilogue (r-th largest of the S*32 slot maxima)
+// ---------------------------------------------------------------------------------------------
+// The slot maxima are a subset of the sample scores, so their r-th largest is <= the sample's
+// r-th largest: a slightly permissive threshold, never a wrong one (the certificate in K4 is
+// what guarantees exactness; the threshold only sizes the candidate list).
+__global__ void __launch_bounds__(256) slot_thr_kernel(const float* __restrict__ slots, int64_t nq, int S, int r,
+                                                       float* __restrict__ thr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = i < S ? slots[(q * S + i) * 32 + lane] : -INFINITY;
+    float best = -INFINITY;
+    for (int it = 0; it < r; it++) {
+        float m = v[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) m = fmaxf(m, v[i]);
+        float wm = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        best = wm;
+        uint32_t owners = __ballot_sync(0xffffffffu, m == wm);
+        if (lane == __ffs(owners) - 1) {  // remove one instance
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (!done && v[i] == wm) { v[i] = -INFINITY; done = true; }
+        }
+    }
+    if (lane == 0) thr[q] = best;
+}
+
+int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st) {
+    if (nq <= 0) return TRX_OK;
+    if (S > 8 || r > 32 * S) { set_error("slot_thr: S=%d r=%d unsupported", S, r); return TRX_EINVAL; }
+    slot_thr_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(slots, nq, S, r, thr);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+}  // namespace trx

@@ -1,0 +1,560 @@
+// trx_api.cu -- the C ABI (include/trx.h) and the host-side search pipeline.
+//
+// Pipeline of one trx_search batch (B <= max_batch queries):
+//
+//   K1 query_prep   fp32 queries -> bf16 (+|q|^2), certificate slack eps
+//   pass 0          scorer over the 1/32 row sample -> per-query threshold thr (target: ~T rows
+//                   of the corpus score above it)
+//   main pass       scorer over the whole bf16 corpus, candidates with score > thr appended
+//                   (K2 tcgen05 for batches, K3 CUDA-core streaming for tiny batches)
+//   K4 rescore      exact fp32 score of the best candidates, certificate, final top-k
+//   fallback        queries without a certificate: K3 fp32 scan + exact radix top-k
+//
+// The fallback is an exact GPU path, not a CPU one: nothing here ever computes on the host.
+#include <float.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace trx {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+static int dmalloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return TRX_OK;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        return TRX_ENOMEM;
+    }
+    return TRX_OK;
+}
+template <typename T>
+static void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ list, int d,
+                                   float* __restrict__ dst) {
+    const int64_t s = list[blockIdx.x];
+    for (int c = threadIdx.x; c < d; c += blockDim.x) dst[(int64_t)blockIdx.x * d + c] = src[s * d + c];
+}
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ list, int n,
+                                  int32_t* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[list[i]];
+}
+
+}  // namespace trx
+
+using namespace trx;
+
+struct trx_index {
+    int d = 0, metric = 0, device = 0, Kp = 0, sm_count = 148;
+    int64_t ntotal = 0, capacity = 0, id_offset = 0;
+    float* x32 = nullptr;            // [capacity, d]   the FAISS-equivalent fp32 store
+    __nv_bfloat16* x16 = nullptr;    // [capacity, Kp]  TMA / streaming copy
+    float* xnorm2 = nullptr;         // [capacity]
+    int32_t* groups = nullptr;       // [capacity] (valid when has_groups)
+    bool has_groups = false;
+    uint32_t* norm2_max = nullptr;   // 1 (float bits)
+    // 1/rate row sample for threshold estimation
+    __nv_bfloat16* xs16 = nullptr; int64_t ns = 0, ns_cap = 0; bool sample_dirty = true;
+    // options
+    int opt_path = TRX_PATH_AUTO;
+    int max_batch = 8192;
+    int target = 512;       // expected candidates per query
+    int sample_rate = 32;
+    int stream_max_batch = 0;  // AUTO: batches <= this use the K3 streaming prefilter
+    int timing = 0;
+    // workspaces (sized for max_batch)
+    int ws_batch = 0, ws_cap = 0;
+    float* q32 = nullptr; __nv_bfloat16* q16 = nullptr; float* qnorm2 = nullptr; float* eps = nullptr;
+    float* thr = nullptr; int32_t* excl = nullptr;
+    Cand* cand = nullptr; uint32_t* cand_cnt = nullptr;
+    float* slots = nullptr; size_t slots_elems = 0;
+    float* Dd = nullptr; int64_t* Id = nullptr; int ws_k = 0;
+    int32_t* fb_list = nullptr; uint32_t* fb_count = nullptr; uint64_t* counters = nullptr;
+    float* qfb = nullptr; int32_t* exfb = nullptr;
+    float* xscores = nullptr; size_t xscores_elems = 0;  // exact-path score rows
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    trx_stats_t st{};
+};
+
+static void free_ws(trx_index* ix) {
+    dfree(ix->q32); dfree(ix->q16); dfree(ix->qnorm2); dfree(ix->eps); dfree(ix->thr); dfree(ix->excl);
+    dfree(ix->cand); dfree(ix->cand_cnt); dfree(ix->slots); dfree(ix->Dd); dfree(ix->Id);
+    dfree(ix->fb_list); dfree(ix->qfb); dfree(ix->exfb); dfree(ix->xscores);
+    ix->ws_batch = ix->ws_cap = ix->ws_k = 0; ix->slots_elems = 0; ix->xscores_elems = 0;
+}
+
+static void free_store(trx_index* ix) {
+    dfree(ix->x32); dfree(ix->x16); dfree(ix->xnorm2); dfree(ix->groups); dfree(ix->xs16);
+    ix->capacity = 0; ix->ntotal = 0; ix->ns = ix->ns_cap = 0; ix->has_groups = false; ix->sample_dirty = true;
+}
+
+static int grow(trx_index* ix, int64_t need) {
+    if (need <= ix->capacity) return TRX_OK;
+    if (need >= (int64_t)1 << 31) { set_error("ntotal %lld exceeds 2^31-1 rows per index", (long long)need); return TRX_EINVAL; }
+    int64_t cap = ix->capacity == 0 ? need : std::max(need, ix->capacity + ix->capacity / 2);
+    float* nx32; __nv_bfloat16* nx16; float* nn2; int32_t* ng;
+    TRX_TRY(dmalloc(&nx32, (size_t)cap * ix->d));
+    if (dmalloc(&nx16, (size_t)cap * ix->Kp) != TRX_OK) { cudaFree(nx32); return TRX_ENOMEM; }
+    if (dmalloc(&nn2, (size_t)cap) != TRX_OK) { cudaFree(nx32); cudaFree(nx16); return TRX_ENOMEM; }
+    if (dmalloc(&ng, (size_t)cap) != TRX_OK) { cudaFree(nx32); cudaFree(nx16); cudaFree(nn2); return TRX_ENOMEM; }
+    if (ix->ntotal > 0) {
+        TRX_CUDA(cudaMemcpy(nx32, ix->x32, (size_t)ix->ntotal * ix->d * 4, cudaMemcpyDeviceToDevice));
+        TRX_CUDA(cudaMemcpy(nx16, ix->x16, (size_t)ix->ntotal * ix->Kp * 2, cudaMemcpyDeviceToDevice));
+        TRX_CUDA(cudaMemcpy(nn2, ix->xnorm2, (size_t)ix->ntotal * 4, cudaMemcpyDeviceToDevice));
+        if (ix->has_groups) TRX_CUDA(cudaMemcpy(ng, ix->groups, (size_t)ix->ntotal * 4, cudaMemcpyDeviceToDevice));
+    }
+    dfree(ix->x32); dfree(ix->x16); dfree(ix->xnorm2); dfree(ix->groups);
+    ix->x32 = nx32; ix->x16 = nx16; ix->xnorm2 = nn2; ix->groups = ng; ix->capacity = cap;
+    return TRX_OK;
+}
+
+static int candidate_cap(const trx_index* ix, int k) {
+    int T = std::max(ix->target, 4 * k);
+    int cap = 4 * T;
+    int p = 1024;
+    while (p < cap) p <<= 1;
+    return p;
+}
+
+static int ensure_ws(trx_index* ix, int B, int k, int cap) {
+    if (B > ix->ws_batch || cap > ix->ws_cap) {
+        int nb = std::max(B, ix->ws_batch), nc = std::max(cap, ix->ws_cap);
+        dfree(ix->q32); dfree(ix->q16); dfree(ix->qnorm2); dfree(ix->eps); dfree(ix->thr); dfree(ix->excl);
+        dfree(ix->cand); dfree(ix->cand_cnt); dfree(ix->fb_list); dfree(ix->qfb); dfree(ix->exfb);
+        dfree(ix->Dd); dfree(ix->Id); ix->ws_k = 0;
+        TRX_TRY(dmalloc(&ix->q32, (size_t)nb * ix->d));
+        TRX_TRY(dmalloc(&ix->q16, (size_t)nb * ix->Kp));
+        TRX_TRY(dmalloc(&ix->qnorm2, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->eps, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->thr, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->excl, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->cand, (size_t)nb * nc));
+        TRX_TRY(dmalloc(&ix->cand_cnt, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->fb_list, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->qfb, (size_t)nb * ix->d));
+        TRX_TRY(dmalloc(&ix->exfb, (size_t)nb));
+        ix->ws_batch = nb; ix->ws_cap = nc;
+    }
+    if (k > ix->ws_k) {
+        dfree(ix->Dd); dfree(ix->Id);
+        TRX_TRY(dmalloc(&ix->Dd, (size_t)ix->ws_batch * k));
+        TRX_TRY(dmalloc(&ix->Id, (size_t)ix->ws_batch * k));
+        ix->ws_k = k;
+    }
+    return TRX_OK;
+}
+
+static int ensure_sample(trx_index* ix, cudaStream_t st) {
+    if (!ix->sample_dirty) return TRX_OK;
+    int64_t ns = (ix->ntotal + ix->sample_rate - 1) / ix->sample_rate;
+    if (ns > ix->ns_cap) {
+        dfree(ix->xs16);
+        TRX_TRY(dmalloc(&ix->xs16, (size_t)ns * ix->Kp));
+        ix->ns_cap = ns;
+    }
+    ix->ns = ns;
+    TRX_TRY(launch_sample_gather(ix->x16, ix->ntotal, ix->Kp, ix->sample_rate, ix->xs16, ns, st));
+    ix->sample_dirty = false;
+    return TRX_OK;
+}
+
+// exact path for nq queries whose fp32 rows are qdev[nq][d]; results to Dd/Id rows qmap[i] (or i).
+static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, const int32_t* qmap_dev, int64_t nq,
+                     int k, cudaStream_t st) {
+    const int64_t N = ix->ntotal;
+    size_t budget = (size_t)64 << 20;  // floats (256 MB)
+    int64_t rows = (int64_t)std::max<size_t>(8, std::min<size_t>(1024, budget / (size_t)N));
+    rows = std::min<int64_t>(rows, std::max<int64_t>(nq, 1));
+    if ((size_t)rows * N > ix->xscores_elems) {
+        dfree(ix->xscores);
+        TRX_TRY(dmalloc(&ix->xscores, (size_t)rows * N));
+        ix->xscores_elems = (size_t)rows * N;
+    }
+    for (int64_t q0 = 0; q0 < nq; q0 += rows) {
+        int64_t nb = std::min(rows, nq - q0);
+        StreamArgs a{};
+        a.x = ix->x32; a.pitch = ix->d; a.n = N; a.d = ix->d;
+        a.q32 = qdev + q0 * ix->d; a.q_pitch = ix->d; a.nq = nb;
+        a.groups = ix->has_groups ? ix->groups : nullptr;
+        a.excl = (excl_dev && ix->has_groups) ? excl_dev + q0 : nullptr;
+        a.out = ix->xscores; a.out_ld = N;
+        a.metric = ix->metric; a.bf16 = false; a.append = false;
+        TRX_TRY(launch_stream(a, ix->sm_count, st));
+        TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, k, ix->metric == TRX_METRIC_L2, ix->id_offset,
+                                  qmap_dev ? qmap_dev + q0 : nullptr,
+                                  qmap_dev ? ix->Dd : ix->Dd + q0 * k, qmap_dev ? ix->Id : ix->Id + q0 * k, st));
+    }
+    ix->st.queries_exact += nq;
+    return TRX_OK;
+}
+
+static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, int k, const int32_t* excl,
+                        bool excl_dev, float* D, int64_t* I, bool out_dev, cudaStream_t st) {
+    const int64_t N = ix->ntotal;
+    const int cap = candidate_cap(ix, k);
+    TRX_TRY(ensure_ws(ix, (int)B, k, cap));
+
+    // queries / exclusion list on the device
+    const float* qdev = xq;
+    if (!xq_dev) {
+        TRX_CUDA(cudaMemcpyAsync(ix->q32, xq, (size_t)B * ix->d * 4, cudaMemcpyHostToDevice, st));
+        qdev = ix->q32;
+    }
+    const int32_t* exdev = nullptr;
+    if (excl && ix->has_groups) {
+        if (excl_dev) exdev = excl;
+        else {
+            TRX_CUDA(cudaMemcpyAsync(ix->excl, excl, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+            exdev = ix->excl;
+        }
+    }
+
+    int path = ix->opt_path;
+    if (path == TRX_PATH_AUTO) {
+        if (N <= 8192 || k > 256) path = TRX_PATH_EXACT;
+        else if (B <= ix->stream_max_batch) path = TRX_PATH_STREAM;
+        else path = TRX_PATH_UMMA;
+    } else if (path != TRX_PATH_EXACT && (N <= 2 * (int64_t)cap || k > 256)) {
+        path = TRX_PATH_EXACT;  // prefilter needs a corpus larger than the candidate list
+    }
+    ix->st.last_path = path;
+    if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[0], st));
+
+    if (path == TRX_PATH_EXACT) {
+        TRX_TRY(run_exact(ix, qdev, exdev, nullptr, B, k, st));
+    } else {
+        TRX_TRY(ensure_sample(ix, st));
+        TRX_TRY(launch_query_prep(qdev, B, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, st));
+        TRX_TRY(launch_eps(ix->qnorm2, ix->norm2_max, B, ix->d, ix->metric, ix->eps, st));
+        TRX_CUDA(cudaMemsetAsync(ix->cand_cnt, 0, (size_t)B * 4, st));
+        TRX_CUDA(cudaMemsetAsync(ix->fb_count, 0, 4, st));
+        const int T = std::max(ix->target, 4 * k);
+        int r = std::max(1, (T + ix->sample_rate / 2) / ix->sample_rate);
+
+        if (path == TRX_PATH_UMMA) {
+            const int S = umma_num_slices(ix->ns);
+            size_t need = (size_t)B * S * 32;
+            if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
+            UmmaArgs u{};
+            u.q16 = ix->q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
+            u.mode = 2; u.out = ix->slots;
+            TRX_TRY(launch_umma(u, ix->sm_count, st));
+            TRX_TRY(launch_slot_thr(ix->slots, B, S, std::min(r, 32 * S), ix->thr, st));
+            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[1], st));
+            u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
+            u.thr = ix->thr; u.cand = ix->cand; u.cand_cnt = ix->cand_cnt; u.cap = cap;
+            TRX_TRY(launch_umma(u, ix->sm_count, st));
+            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[2], st));
+        } else {
+            size_t need = (size_t)B * ix->ns;
+            if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
+            StreamArgs a{};
+            a.x = ix->xs16; a.pitch = ix->Kp; a.n = ix->ns; a.d = ix->Kp;
+            a.q16 = ix->q16; a.q_pitch = ix->Kp; a.nq = B;
+            a.out = ix->slots; a.out_ld = ix->ns; a.metric = TRX_METRIC_INNER_PRODUCT; a.bf16 = true; a.append = false;
+            TRX_TRY(launch_stream(a, ix->sm_count, st));
+            TRX_TRY(launch_row_kth(ix->slots, ix->ns, ix->ns, B, (int)std::min<int64_t>(r, ix->ns), ix->thr, st));
+            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[1], st));
+            a.x = ix->x16; a.n = N; a.out = nullptr; a.append = true;
+            a.thr = ix->thr; a.cand = ix->cand; a.cand_cnt = ix->cand_cnt; a.cap = cap;
+            TRX_TRY(launch_stream(a, ix->sm_count, st));
+            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[2], st));
+        }
+
+        RescoreArgs ra{};
+        ra.cand = ix->cand; ra.cand_cnt = ix->cand_cnt; ra.cap = cap; ra.thr = ix->thr; ra.eps = ix->eps;
+        ra.x32 = ix->x32; ra.d = ix->d; ra.n = N; ra.q32 = qdev; ra.nq = B;
+        ra.groups = ix->has_groups ? ix->groups : nullptr; ra.excl = exdev;
+        ra.k = k; ra.metric = ix->metric; ra.id_offset = ix->id_offset;
+        ra.D = ix->Dd; ra.I = ix->Id; ra.fb_list = ix->fb_list; ra.fb_count = ix->fb_count; ra.counters = ix->counters;
+        TRX_TRY(launch_rescore(ra, st));
+
+        uint32_t nfb = 0;
+        TRX_CUDA(cudaMemcpyAsync(&nfb, ix->fb_count, 4, cudaMemcpyDeviceToHost, st));
+        TRX_CUDA(cudaStreamSynchronize(st));
+        if (nfb > 0) {
+            gather_rows_kernel<<<nfb, 128, 0, st>>>(qdev, ix->fb_list, ix->d, ix->qfb);
+            count_launch();
+            const int32_t* exfb = nullptr;
+            if (exdev) {
+                gather_i32_kernel<<<(nfb + 255) / 256, 256, 0, st>>>(exdev, ix->fb_list, (int)nfb, ix->exfb);
+                count_launch();
+                exfb = ix->exfb;
+            }
+            TRX_CUDA(cudaGetLastError());
+            TRX_TRY(run_exact(ix, ix->qfb, exfb, ix->fb_list, nfb, k, st));
+        }
+    }
+    if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[3], st));
+
+    TRX_CUDA(cudaMemcpyAsync(D, ix->Dd, (size_t)B * k * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    TRX_CUDA(cudaMemcpyAsync(I, ix->Id, (size_t)B * k * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!out_dev || !xq_dev || ix->timing) TRX_CUDA(cudaStreamSynchronize(st));
+    if (ix->timing) {
+        float ms = 0.f;
+        TRX_CUDA(cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]));
+        ix->st.last_total_ms = ms;
+        if (path != TRX_PATH_EXACT) {
+            TRX_CUDA(cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]));
+            ix->st.last_prefilter_ms = ms;
+        } else ix->st.last_prefilter_ms = 0.0;
+    }
+    ix->st.queries += B;
+    return TRX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* trx_last_error(void) { return g_err.c_str(); }
+const char* trx_version(void) { return "textreact_b200 libtrx 0.1 (sm_100a)"; }
+
+int trx_create(int d, int metric, int device, trx_index** out) {
+    if (!out) { set_error("out is null"); return TRX_EINVAL; }
+    *out = nullptr;
+    if (d <= 0 || d > 16384) { set_error("bad dimension %d", d); return TRX_EINVAL; }
+    if (metric != TRX_METRIC_INNER_PRODUCT && metric != TRX_METRIC_L2) { set_error("bad metric %d", metric); return TRX_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: this engine has no CPU fallback");
+        return TRX_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return TRX_EINVAL; }
+    cudaDeviceProp prop;
+    TRX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libtrx is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return TRX_ENODEV;
+    }
+    trx_index* ix = new (std::nothrow) trx_index();
+    if (!ix) { set_error("host allocation failed"); return TRX_ENOMEM; }
+    ix->d = d; ix->metric = metric; ix->device = device; ix->sm_count = prop.multiProcessorCount;
+    int kcols = d + (metric == TRX_METRIC_L2 ? 3 : 0);
+    ix->Kp = (kcols + 63) / 64 * 64;
+    DeviceGuard g(device);
+    int rc = TRX_OK;
+    do {
+        if ((rc = dmalloc(&ix->norm2_max, 1)) != TRX_OK) break;
+        if ((rc = dmalloc(&ix->fb_count, 1)) != TRX_OK) break;
+        if ((rc = dmalloc(&ix->counters, 4)) != TRX_OK) break;
+        if (cudaMemset(ix->norm2_max, 0, 4) != cudaSuccess || cudaMemset(ix->counters, 0, 32) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("device init failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = TRX_ECUDA; break;
+        }
+        for (int i = 0; i < 4; i++)
+            if (cudaEventCreate(&ix->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = TRX_ECUDA; break; }
+    } while (0);
+    if (rc != TRX_OK) { trx_destroy(ix); return rc; }
+    ix->st.sm_count = ix->sm_count;
+    *out = ix;
+    return TRX_OK;
+}
+
+void trx_destroy(trx_index* ix) {
+    if (!ix) return;
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    free_ws(ix); free_store(ix);
+    dfree(ix->norm2_max); dfree(ix->fb_count); dfree(ix->counters);
+    for (int i = 0; i < 4; i++) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+    delete ix;
+}
+
+int trx_reset(trx_index* ix) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    DeviceGuard g(ix->device);
+    TRX_CUDA(cudaDeviceSynchronize());
+    free_store(ix);
+    TRX_CUDA(cudaMemset(ix->norm2_max, 0, 4));
+    return TRX_OK;
+}
+
+int64_t trx_ntotal(const trx_index* ix) { return ix ? ix->ntotal : -1; }
+int trx_dim(const trx_index* ix) { return ix ? ix->d : -1; }
+int trx_metric(const trx_index* ix) { return ix ? ix->metric : -1; }
+
+int trx_reserve(trx_index* ix, int64_t n) {
+    if (!ix || n < 0) { set_error("bad argument"); return TRX_EINVAL; }
+    DeviceGuard g(ix->device);
+    return grow(ix, n);
+}
+
+int trx_add(trx_index* ix, const float* x, int64_t n) {
+    if (!ix || n < 0 || (n > 0 && !x)) { set_error("bad argument"); return TRX_EINVAL; }
+    if (n == 0) return TRX_OK;
+    DeviceGuard g(ix->device);
+    TRX_TRY(grow(ix, ix->ntotal + n));
+    cudaStream_t st = ix->own_stream;
+    float* dst = ix->x32 + ix->ntotal * ix->d;
+    TRX_CUDA(cudaMemcpyAsync(dst, x, (size_t)n * ix->d * 4, is_device_ptr(x) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    TRX_TRY(launch_ingest(dst, n, ix->d, ix->Kp, ix->metric, ix->x16 + ix->ntotal * ix->Kp, ix->xnorm2 + ix->ntotal,
+                          ix->norm2_max, st));
+    TRX_CUDA(cudaStreamSynchronize(st));
+    ix->ntotal += n;
+    ix->sample_dirty = true;
+    ix->has_groups = false;  // groups must cover every row: set them again after the last add
+    return TRX_OK;
+}
+
+int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    if (gsrc == nullptr) { ix->has_groups = false; return TRX_OK; }
+    if (n != ix->ntotal) { set_error("set_groups: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
+    if (n == 0) return TRX_OK;
+    DeviceGuard g(ix->device);
+    TRX_CUDA(cudaMemcpy(ix->groups, gsrc, (size_t)n * 4, is_device_ptr(gsrc) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    ix->has_groups = true;
+    return TRX_OK;
+}
+
+int trx_set_id_offset(trx_index* ix, int64_t offset) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    ix->id_offset = offset;
+    return TRX_OK;
+}
+
+int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t* excl, float* D, int64_t* I,
+               void* cuda_stream) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    if (nq < 0 || k <= 0) { set_error("bad nq=%lld or k=%d", (long long)nq, k); return TRX_EINVAL; }
+    if (nq == 0) return TRX_OK;
+    if (!xq || !D || !I) { set_error("null buffer"); return TRX_EINVAL; }
+    if (k > 2048) { set_error("k=%d exceeds the supported maximum 2048", k); return TRX_EINVAL; }
+    if (excl && !ix->has_groups) { set_error("exclude given but no groups set (trx_set_groups)"); return TRX_EINVAL; }
+    DeviceGuard g(ix->device);
+    const bool xq_dev = is_device_ptr(xq), out_dev = is_device_ptr(D), excl_dev = is_device_ptr(excl);
+    if (out_dev != is_device_ptr(I)) { set_error("D and I must both be host or both be device pointers"); return TRX_EINVAL; }
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
+    ix->st.searches++;
+    if (ix->ntotal == 0) {  // FAISS: empty index -> all -1
+        std::vector<float> dfill((size_t)nq * k, ix->metric == TRX_METRIC_L2 ? FLT_MAX : -FLT_MAX);
+        std::vector<int64_t> ifill((size_t)nq * k, -1);
+        TRX_CUDA(cudaMemcpy(D, dfill.data(), dfill.size() * 4, out_dev ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+        TRX_CUDA(cudaMemcpy(I, ifill.data(), ifill.size() * 8, out_dev ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+        return TRX_OK;
+    }
+    for (int64_t q0 = 0; q0 < nq; q0 += ix->max_batch) {
+        int64_t B = std::min<int64_t>(ix->max_batch, nq - q0);
+        TRX_TRY(search_batch(ix, xq + q0 * ix->d, xq_dev, B, k, excl ? excl + q0 : nullptr, excl_dev, D + q0 * k,
+                             I + q0 * k, out_dev, st));
+    }
+    return TRX_OK;
+}
+
+int trx_set_option(trx_index* ix, const char* key, double v) {
+    if (!ix || !key) { set_error("bad argument"); return TRX_EINVAL; }
+    if (!strcmp(key, "path")) {
+        if (v < 0 || v > 3) { set_error("path must be 0..3"); return TRX_EINVAL; }
+        ix->opt_path = (int)v;
+    } else if (!strcmp(key, "max_batch")) {
+        if (v < 1 || v > 65536) { set_error("max_batch out of range"); return TRX_EINVAL; }
+        ix->max_batch = (int)v;
+    } else if (!strcmp(key, "target_candidates")) {
+        if (v < 32 || v > 4096) { set_error("target_candidates out of range"); return TRX_EINVAL; }
+        ix->target = (int)v;
+    } else if (!strcmp(key, "sample_rate")) {
+        if (v < 2 || v > 1024) { set_error("sample_rate out of range"); return TRX_EINVAL; }
+        ix->sample_rate = (int)v; ix->sample_dirty = true;
+    } else if (!strcmp(key, "stream_max_batch")) {
+        ix->stream_max_batch = (int)v;
+    } else if (!strcmp(key, "timing")) {
+        ix->timing = v != 0;
+    } else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
+    return TRX_OK;
+}
+
+int trx_get_option(const trx_index* ix, const char* key, double* v) {
+    if (!ix || !key || !v) { set_error("bad argument"); return TRX_EINVAL; }
+    if (!strcmp(key, "path")) *v = ix->opt_path;
+    else if (!strcmp(key, "max_batch")) *v = ix->max_batch;
+    else if (!strcmp(key, "target_candidates")) *v = ix->target;
+    else if (!strcmp(key, "sample_rate")) *v = ix->sample_rate;
+    else if (!strcmp(key, "stream_max_batch")) *v = ix->stream_max_batch;
+    else if (!strcmp(key, "timing")) *v = ix->timing;
+    else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
+    return TRX_OK;
+}
+
+int trx_stats(const trx_index* ix, trx_stats_t* out) {
+    if (!ix || !out) { set_error("bad argument"); return TRX_EINVAL; }
+    DeviceGuard g(ix->device);
+    uint64_t c[4];
+    TRX_CUDA(cudaMemcpy(c, ix->counters, 32, cudaMemcpyDeviceToHost));
+    *out = ix->st;
+    out->rescored = (int64_t)c[0]; out->queries_uncert = (int64_t)c[1]; out->queries_overflow = (int64_t)c[2];
+    out->candidates = (int64_t)c[3];
+    out->launches = g_launches.load();
+    return TRX_OK;
+}
+
+int trx_merge_topk(int metric, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, float* D, int64_t* I,
+                   void* cuda_stream) {
+    if (G <= 0 || nq < 0 || k <= 0 || !Dg || !Ig || !D || !I) { set_error("bad argument"); return TRX_EINVAL; }
+    if (!is_device_ptr(Dg) || !is_device_ptr(Ig) || !is_device_ptr(D) || !is_device_ptr(I)) {
+        set_error("trx_merge_topk takes device pointers");
+        return TRX_EINVAL;
+    }
+    return launch_merge(metric, Dg, Ig, G, nq, k, D, I, (cudaStream_t)cuda_stream);
+}
+
+int trx_debug_scores_umma(trx_index* ix, const float* xq, int64_t nq, int64_t row0, int64_t n, float* out,
+                          void* cuda_stream) {
+    if (!ix || !xq || !out || nq <= 0 || n <= 0 || row0 < 0 || row0 + n > ix->ntotal) { set_error("bad argument"); return TRX_EINVAL; }
+    if (!is_device_ptr(xq) || !is_device_ptr(out)) { set_error("debug_scores takes device pointers"); return TRX_EINVAL; }
+    DeviceGuard g(ix->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
+    TRX_TRY(ensure_ws(ix, (int)nq, 1, candidate_cap(ix, 1)));
+    TRX_TRY(launch_query_prep(xq, nq, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, st));
+    UmmaArgs u{};
+    u.q16 = ix->q16; u.nq = nq; u.x16 = ix->x16 + row0 * ix->Kp; u.n = n; u.Kp = ix->Kp;
+    u.mode = 0; u.out = out; u.out_ld = n;
+    TRX_TRY(launch_umma(u, ix->sm_count, st));
+    TRX_CUDA(cudaStreamSynchronize(st));
+    return TRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""FAISS flat-index surface over the B200 engine.
+
+Mirrors exactly what TextReact's retrieval script calls on the ``faiss`` object
+(reference: retrieve/retrieve_faiss.py:62-74):
+
+    index = faiss.IndexFlatL2(d)            # :65   (IndexFlatIP for the 768-d neural retriever)
+    index.add(train_fps)                    # :66
+    distance, rank = index.search(query_fps, k)   # :71
+
+Inputs of any numeric dtype / memory order are coerced with
+``np.ascontiguousarray(x, dtype='float32')`` as FAISS's python wrapper does -- the script
+passes int64 difference fingerprints (:26) and int8 Morgan bits (:40).  A wrong second
+dimension raises ``AssertionError`` (FAISS behaviour); engine failures raise ``RuntimeError``
+/ ``MemoryError``.  Extensions, all keyword-only and ignored by the reference script:
+``exclude=`` (gold-removed mode, textreact/dataset.py:74-76 lifted into the engine),
+``set_groups``, torch CUDA tensors in / out, ``device=``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import PATH_AUTO, PATH_EXACT, PATH_STREAM, PATH_UMMA  # noqa: F401
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+
+try:  # torch is plumbing only (device tensors, streams); numpy callers never need it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _as_f32_matrix(x, d):
+    """-> (pointer, n, keepalive, on_device)"""
+    if _is_torch(x) and x.is_cuda:
+        assert x.dim() == 2 and x.shape[1] == d, f"expected shape [n, {d}], got {tuple(x.shape)}"
+        t = x.detach().to(torch.float32).contiguous()
+        return t.data_ptr(), t.shape[0], t, True
+    if _is_torch(x):
+        x = x.detach().cpu().numpy()
+    a = np.ascontiguousarray(x, dtype="float32")
+    assert a.ndim == 2 and a.shape[1] == d, f"expected shape [n, {d}], got {a.shape}"
+    return a.ctypes.data, a.shape[0], a, False
+
+
+def _as_i32_vector(x, n, what):
+    if _is_torch(x) and x.is_cuda:
+        t = x.detach().to(torch.int32).contiguous()
+        assert t.dim() == 1 and t.shape[0] == n, f"{what}: expected {n} entries, got {tuple(t.shape)}"
+        return t.data_ptr(), t
+    if _is_torch(x):
+        x = x.detach().cpu().numpy()
+    a = np.ascontiguousarray(x, dtype=np.int32)
+    assert a.ndim == 1 and a.shape[0] == n, f"{what}: expected {n} entries, got {a.shape}"
+    return a.ctypes.data, a
+
+
+class IndexFlat:
+    """Exact (brute-force) index; ``metric`` is METRIC_L2 (squared distances, ascending) or
+    METRIC_INNER_PRODUCT (scores, descending)."""
+
+    def __init__(self, d, metric=METRIC_L2, *, device=None):
+        L = _lib.lib()
+        if device is None:
+            device = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
+        self._h = ctypes.c_void_p()
+        self._L = L
+        _lib.check(L.trx_create(int(d), int(metric), int(device), ctypes.byref(self._h)), "IndexFlat")
+        self.d = int(d)
+        self.metric_type = int(metric)
+        self.is_trained = True
+        self.device = int(device)
+
+    # -- FAISS attributes -------------------------------------------------------------------
+    @property
+    def ntotal(self):
+        return int(self._L.trx_ntotal(self._h))
+
+    # -- FAISS methods ----------------------------------------------------------------------
+    def add(self, x):
+        ptr, n, keep, _ = _as_f32_matrix(x, self.d)
+        _lib.check(self._L.trx_add(self._h, ptr, n), "add")
+        del keep
+
+    def search(self, x, k, *, D=None, I=None, exclude=None, params=None):
+        assert k > 0
+        ptr, nq, keep, on_dev = _as_f32_matrix(x, self.d)
+        ex_ptr, ex_keep = (None, None)
+        if exclude is not None:
+            ex_ptr, ex_keep = _as_i32_vector(exclude, nq, "exclude")
+        stream = None
+        if on_dev:
+            Dt = D if D is not None else torch.empty((nq, k), dtype=torch.float32, device=keep.device)
+            It = I if I is not None else torch.empty((nq, k), dtype=torch.int64, device=keep.device)
+            assert Dt.shape == (nq, k) and It.shape == (nq, k) and Dt.is_contiguous() and It.is_contiguous()
+            assert Dt.dtype == torch.float32 and It.dtype == torch.int64 and Dt.is_cuda and It.is_cuda
+            dptr, iptr = Dt.data_ptr(), It.data_ptr()
+            stream = torch.cuda.current_stream(keep.device).cuda_stream
+            out = (Dt, It)
+        else:
+            Dn = D if D is not None else np.empty((nq, k), dtype=np.float32)
+            In = I if I is not None else np.empty((nq, k), dtype=np.int64)
+            assert Dn.shape == (nq, k) and In.shape == (nq, k)
+            assert Dn.dtype == np.float32 and In.dtype == np.int64
+            assert Dn.flags.c_contiguous and In.flags.c_contiguous
+            dptr, iptr = Dn.ctypes.data, In.ctypes.data
+            out = (Dn, In)
+        _lib.check(self._L.trx_search(self._h, ptr, nq, int(k), ex_ptr, dptr, iptr, stream), "search")
+        del keep, ex_keep
+        return out
+
+    def reset(self):
+        _lib.check(self._L.trx_reset(self._h), "reset")
+
+    # -- extensions -------------------------------------------------------------------------
+    def reserve(self, n):
+        _lib.check(self._L.trx_reserve(self._h, int(n)), "reserve")
+
+    def set_groups(self, groups):
+        """Per-row exclusion group (text-dedup group / patent id), one int32 per added row."""
+        if groups is None:
+            _lib.check(self._L.trx_set_groups(self._h, None, 0), "set_groups")
+            return
+        ptr, keep = _as_i32_vector(groups, self.ntotal, "groups")
+        _lib.check(self._L.trx_set_groups(self._h, ptr, self.ntotal), "set_groups")
+        del keep
+
+    def set_id_offset(self, offset):
+        _lib.check(self._L.trx_set_id_offset(self._h, int(offset)), "set_id_offset")
+
+    def set_option(self, key, value):
+        _lib.check(self._L.trx_set_option(self._h, key.encode(), float(value)), f"set_option({key})")
+
+    def get_option(self, key):
+        v = ctypes.c_double()
+        _lib.check(self._L.trx_get_option(self._h, key.encode(), ctypes.byref(v)), f"get_option({key})")
+        return v.value
+
+    def stats(self):
+        s = _lib.TrxStats()
+        _lib.check(self._L.trx_stats(self._h, ctypes.byref(s)), "stats")
+        return s.as_dict()
+
+    def debug_scores_umma(self, xq, row0, n):
+        """bf16 tcgen05 scores of CUDA tensor ``xq`` against rows [row0, row0+n) (tests only)."""
+        ptr, nq, keep, on_dev = _as_f32_matrix(xq, self.d)
+        assert on_dev, "debug_scores_umma takes a CUDA tensor"
+        out = torch.empty((nq, n), dtype=torch.float32, device=keep.device)
+        _lib.check(self._L.trx_debug_scores_umma(self._h, ptr, nq, int(row0), int(n), out.data_ptr(),
+                                                 torch.cuda.current_stream(keep.device).cuda_stream), "debug_scores")
+        return out
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.trx_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class IndexFlatIP(IndexFlat):
+    def __init__(self, d, **kw):
+        super().__init__(d, METRIC_INNER_PRODUCT, **kw)
+
+
+class IndexFlatL2(IndexFlat):
+    def __init__(self, d, **kw):
+        super().__init__(d, METRIC_L2, **kw)
+
+
+def merge_topk(Dg, Ig, metric):
+    """K5: merge per-shard results.  Dg [G, nq, k] float32, Ig [G, nq, k] int64 CUDA tensors,
+    every list best-first with global ids, shards in ascending id order."""
+    assert _is_torch(Dg) and Dg.is_cuda and Ig.is_cuda and Dg.shape == Ig.shape and Dg.dim() == 3
+    Dg, Ig = Dg.contiguous(), Ig.contiguous()
+    G, nq, k = Dg.shape
+    D = torch.empty((nq, k), dtype=torch.float32, device=Dg.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=Dg.device)
+    L = _lib.lib()
+    _lib.check(L.trx_merge_topk(int(metric), Dg.data_ptr(), Ig.data_ptr(), G, nq, k, D.data_ptr(), I.data_ptr(),
+                                torch.cuda.current_stream(Dg.device).cuda_stream), "merge_topk")
+    return D, I

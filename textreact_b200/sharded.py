@@ -1,0 +1,76 @@
+"""Row-sharded multi-GPU search: one process per GPU, one exchange step.
+
+No reference counterpart (the reference's retrieval is single-process CPU FAISS,
+retrieve/retrieve_faiss.py:62-74); this is SURVEY.md section 8e / north_star (4):
+shard g of G holds corpus rows [g*N/G, (g+1)*N/G) and answers every query with a local exact
+top-k carrying GLOBAL ids; one all-gather of the [nq, k] score and id lists (NCCL over
+NVLink/NVSwitch) feeds the device k-way merge (K5, ``trx_merge_topk``).  Every rank ends up
+with the full result.
+
+``local_factory`` / ``merge_fn`` are seams for the CPU (gloo) tests of the host logic; the
+defaults are the CUDA engine and there is no CPU fallback behind them.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .index import IndexFlat, merge_topk
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous, near-even split: rows [lo, hi) of shard ``rank``."""
+    return rank * n // world, (rank + 1) * n // world
+
+
+class ShardedIndexFlat:
+    def __init__(self, d, metric, *, group=None, local_factory=None, merge_fn=None, device=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.d, self.metric_type = int(d), int(metric)
+        self.local = (local_factory or (lambda d_, m_: IndexFlat(d_, m_, device=device)))(d, metric)
+        self._merge = merge_fn or merge_topk
+        self._ntotal_global = 0
+        self._lo = 0
+
+    @property
+    def ntotal(self):
+        return self._ntotal_global
+
+    def add_global(self, x):
+        """Every rank is handed the same [N, d] array (or a lazily sliced view); keeps its slice."""
+        n = x.shape[0]
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        self.add_shard(x[lo:hi], lo, n)
+
+    def add_shard(self, x_local, lo, n_global):
+        """This rank's rows are global rows [lo, lo + len(x_local))."""
+        assert self.local.ntotal == 0, "one shard per index"
+        self.local.add(x_local)
+        self.local.set_id_offset(lo)
+        self._lo, self._ntotal_global = int(lo), int(n_global)
+
+    def set_groups_global(self, groups):
+        lo, hi = self._lo, self._lo + self.local.ntotal
+        self.local.set_groups(groups[lo:hi])
+
+    def search(self, xq, k, *, exclude=None):
+        """xq replicated on every rank.  Returns (D, I) on every rank."""
+        D, I = self.local.search(xq, k, exclude=exclude)
+        as_numpy = not isinstance(D, torch.Tensor)
+        if as_numpy:
+            D, I = torch.from_numpy(D), torch.from_numpy(I)
+        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+        Dm, Im = self._merge(Dg, Ig, self.metric_type)
+        if as_numpy and isinstance(Dm, torch.Tensor):
+            return Dm.cpu().numpy(), Im.cpu().numpy()
+        return Dm, Im
+
+    def close(self):
+        if hasattr(self.local, "close"):
+            self.local.close()
