@@ -70,6 +70,18 @@ def test_prefilter_paths_gaussian(metric, path_name):
     assert st["queries_exact"] <= nq // 10, st      # the certificate should hold for almost all
 
 
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_uncertified_queries_take_exact_second_chance(metric):
+    """Starve the candidate lists so the certificate fails for many queries: they must still come back
+    exact, through the threshold-guided fp32 pass or the generic scan."""
+    trx = _engine()
+    n, d, nq, k = 60000, 768, 200, 20
+    xb, xq = util.gaussian(n, d, 15), util.gaussian(nq, d, 16)
+    D, I, st = _run(xb, xq, k, metric, trx.PATH_UMMA, target_candidates=32)
+    oracle.check_parity(D, I, xb, xq, k, metric)
+    assert st["queries_uncert"] > 0 and st["queries_exact"] > 0, st
+
+
 def test_config1_c1_shape():
     """BASELINE.json configs[0]: 100K x 768 fp32 corpus, 1K queries, k=20, inner product."""
     trx = _engine()

@@ -59,7 +59,13 @@ struct __align__(8) Cand {
     int32_t row;
 };
 
-constexpr int kSampleRank = 16;  // threshold = this rank of the sample's scores
+// One threshold hit logged by a K2 epilogue thread.
+struct __align__(16) HitRec {
+    int32_t q;     // query (row of the batch)
+    int32_t row;   // corpus row (local)
+    float score;
+    int32_t pad;
+};
 
 // ---- host launchers (each returns TRX_*) ---------------------------------------------------
 
@@ -110,13 +116,16 @@ struct RescoreArgs {
     int k; int metric; int64_t id_offset;
     float* D; int64_t* I;
     int32_t* fb_list; uint32_t* fb_count;  // queries that need the exact scan
+    float* fb_thr;      // per fb_list entry: exact score every true top-k row must reach (-inf: unknown)
+    const float* eps_acc;  // fp32 summation slack per query (subtracted from fb_thr)
+    const int32_t* qmap;   // nullable: output row / fb_list value of query i is qmap[i]
     uint64_t* counters;                     // [0] rescored rows [1] uncertified [2] overflow [3] candidates
 };
 int launch_rescore(const RescoreArgs& a, cudaStream_t st);
 
 // certificate slack: eps[q] = c * |q| * max|x| (IP) ; L2 doubles it and adds norm slack.
 int launch_eps(const float* qnorm2, const uint32_t* norm2_max_bits, int64_t nq, int d, int metric,
-               float* eps, cudaStream_t st);
+               float* eps, float* eps_acc, cudaStream_t st);
 
 // K2: tcgen05 scoring GEMM.  A = queries bf16 [nq, Kp], B = rows bf16 [n, Kp].
 struct UmmaArgs {
@@ -127,8 +136,10 @@ struct UmmaArgs {
     int mode;
     float* out; int64_t out_ld;
     const float* thr; Cand* cand; uint32_t* cand_cnt; int cap;
+    HitRec* log; uint32_t* log_cnt; int log_cap;   // mode 1: [umma_grid*128][log_cap] private hit logs
 };
 int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st);
+int umma_grid(int64_t nq, int64_t n, int sm_count);  // CTAs the THRESH pass will launch
 int umma_init();  // resolves cuTensorMapEncodeTiled
 int umma_num_slices(int64_t n);  // S of the SLOTMAX mode (out = slots[nq][S][32])
 // r-th largest of the S*32 slot maxima of each query -> thr

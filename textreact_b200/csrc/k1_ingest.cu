@@ -159,21 +159,27 @@ int launch_query_prep(const float* q, int64_t B, int d, int Kp, int metric, __nv
 //   L2 : prefilter score is 2 q.x - |x|^2  ->  2x the IP slack, + 2^-22 max|x|^2 for the 3-way norm
 //        split and + 2^-21 (|q|^2 + max|x|^2) for the fp32 evaluation of |q|^2 - sum (q-x)^2.
 __global__ void k1_eps_kernel(const float* __restrict__ qnorm2, const uint32_t* __restrict__ norm2_max_bits,
-                              int64_t nq, int d, int metric, float* __restrict__ eps) {
+                              int64_t nq, int d, int metric, float* __restrict__ eps, float* __restrict__ eps_acc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     float xm2 = __uint_as_float(*norm2_max_bits);
     float qn = sqrtf(qnorm2[i]) * 1.000001f, xn = sqrtf(xm2) * 1.000001f;
-    float c = 0.00390625f * 1.002f + 2.f * (float)(d + 3) * 1.1920929e-7f;
-    float e = c * qn * xn;
-    if (metric == TRX_METRIC_L2) e = 2.f * e + 2.4e-7f * xm2 + 4.8e-7f * (qnorm2[i] + xm2);
+    float cacc = 2.f * (float)(d + 3) * 1.1920929e-7f;
+    float c = 0.00390625f * 1.002f + cacc;
+    float e = c * qn * xn, ea = cacc * qn * xn;
+    if (metric == TRX_METRIC_L2) {
+        float extra = 2.4e-7f * xm2 + 4.8e-7f * (qnorm2[i] + xm2);
+        e = 2.f * e + extra;
+        ea = cacc * (qnorm2[i] + xm2) * 2.f + extra;  // sum (q-x)^2 <= 2(|q|^2+|x|^2)
+    }
     eps[i] = e * 1.0001f + 1e-37f;
+    eps_acc[i] = ea * 1.0001f + 1e-37f;   // two fp32 evaluations of the same score differ by at most this
 }
 
 int launch_eps(const float* qnorm2, const uint32_t* norm2_max_bits, int64_t nq, int d, int metric, float* eps,
-               cudaStream_t st) {
+               float* eps_acc, cudaStream_t st) {
     if (nq <= 0) return TRX_OK;
-    k1_eps_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(qnorm2, norm2_max_bits, nq, d, metric, eps);
+    k1_eps_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(qnorm2, norm2_max_bits, nq, d, metric, eps, eps_acc);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;

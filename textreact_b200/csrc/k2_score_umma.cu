@@ -14,7 +14,9 @@
 //   warps 4-7 epilogue: tcgen05.ld 32x32b.x32, one query row per thread
 // Epilogue modes:
 //   STORE    fp32 scores to HBM (tests / profiling only)
-//   THRESH   compare against the per-query threshold, append (score,row) candidates (rare path)
+//   THRESH   compare against the per-query threshold; hits go to a per-thread private log in HBM with
+//            a register cursor (no atomics, fire-and-forget 16-byte stores), and a scatter kernel
+//            turns the logs into per-query candidate lists afterwards
 //   SLOTMAX  running max of every (column mod 32) slot -> threshold estimation on the sample
 #include <cudaTypedefs.h>
 
@@ -119,7 +121,8 @@ struct KParams {
     int KB;          // k-blocks
     int MT, NT, S;   // query tiles, row tiles, slices (S == NT for STORE/THRESH)
     float* out; int64_t out_ld;
-    const float* thr; Cand* cand; uint32_t* cand_cnt; int cap;
+    const float* thr; uint32_t* cand_cnt;
+    HitRec* log; uint32_t* log_cnt; int log_cap;   // THRESH: [grid*128][log_cap] private hit logs
     float* slots;    // SLOTMAX: [nq][S][32]
 };
 
@@ -219,6 +222,9 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // ===================== epilogue =====================
         const int wq = warp & 3;  // TMEM lane quarter this warp may access
         int as = 0; uint32_t aphase = 0;
+        const int64_t log_id = (int64_t)blockIdx.x * 128 + (threadIdx.x - 128);
+        HitRec* my_log = MODE == MODE_THRESH ? p.log + log_id * p.log_cap : nullptr;
+        uint32_t nlog = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int mt = u % p.MT, sl = u / p.MT;
             const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
@@ -236,11 +242,9 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 tc_fence_after();
                 const int64_t col0 = (int64_t)nt * BN;
                 const bool full_tile = col0 + BN <= p.n;
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch++) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
-                    tc_wait_ld();
+                const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN);
+                // One 32-column chunk of this thread's query row.
+                auto process = [&](const uint32_t (&v)[32], int ch) {
                     const int64_t cbase = col0 + ch * 32;
                     if (MODE == MODE_STORE) {
                         if (row_ok) {
@@ -249,18 +253,34 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 if (cbase + j < p.n) p.out[row * p.out_ld + cbase + j] = __uint_as_float(v[j]);
                         }
                     } else if (MODE == MODE_THRESH) {
-                        float mx = __uint_as_float(v[0]);
+                        // common case: nothing in the chunk beats the threshold -> 18 FMNMX + 1 compare
+                        float g[4];
 #pragma unroll
-                        for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        for (int gi = 0; gi < 4; gi++) {
+                            float m = __uint_as_float(v[8 * gi]);
+#pragma unroll
+                            for (int j = 1; j < 8; j++) m = fmaxf(m, __uint_as_float(v[8 * gi + j]));
+                            g[gi] = m;
+                        }
+                        const float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
                         if (mx > thr) {
+                            // rare: scan only the 8-column groups that contain a hit
 #pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                float s = __uint_as_float(v[j]);
-                                if (s > thr && cbase + j < p.n) {
-                                    uint32_t pos = atomicAdd(p.cand_cnt + row, 1u);
-                                    if (pos < (uint32_t)p.cap) {
-                                        Cand c; c.score = s; c.row = (int32_t)(cbase + j);
-                                        p.cand[row * (int64_t)p.cap + pos] = c;
+                            for (int gi = 0; gi < 4; gi++) {
+                                if (g[gi] > thr) {
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) {
+                                        const float sc = __uint_as_float(v[8 * gi + j]);
+                                        const int col = (int)cbase + 8 * gi + j;
+                                        if (sc > thr && (full_tile || col < (int)p.n)) {
+                                            if (nlog < (uint32_t)p.log_cap) {
+                                                int4 rec = make_int4((int)row, col, __float_as_int(sc), 0);
+                                                *reinterpret_cast<int4*>(my_log + nlog) = rec;
+                                            } else {
+                                                atomicOr(p.cand_cnt + row, 0x80000000u);  // log full: query overflowed
+                                            }
+                                            nlog++;
+                                        }
                                     }
                                 }
                             }
@@ -275,9 +295,23 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                 if (cbase + j < p.n) slot[j] = fmaxf(slot[j], __uint_as_float(v[j]));
                         }
                     }
+                };
+                // Software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is scanned.
+                uint32_t va[32], vb[32];
+                tc_ld32(tbase, va);
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch += 2) {
+                    tc_wait_ld();
+                    tc_ld32(tbase + (uint32_t)((ch + 1) * 32), vb);
+                    process(va, ch);
+                    tc_wait_ld();
+                    if (ch + 2 < BN / 32) tc_ld32(tbase + (uint32_t)((ch + 2) * 32), va);
+                    else {  // everything of this accumulator is in registers: hand TMEM back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(as));
+                    }
+                    process(vb, ch + 1);
                 }
-                tc_fence_before();
-                mbar_arrive(tempty_bar(as));
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
             if (MODE == MODE_SLOTMAX && row_ok) {
@@ -287,6 +321,7 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     *reinterpret_cast<float4*>(dst + j) = make_float4(slot[j], slot[j + 1], slot[j + 2], slot[j + 3]);
             }
         }
+        if (MODE == MODE_THRESH) p.log_cnt[log_id] = nlog < (uint32_t)p.log_cap ? nlog : (uint32_t)p.log_cap;
     }
 
     tc_fence_before();
@@ -294,6 +329,28 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// One warp per private log: entries -> per-query candidate lists (the only global atomics of the
+// batched path, ~800 per query, issued with full-chip parallelism instead of from the epilogue).
+__global__ void __launch_bounds__(256) k2_scatter_kernel(const HitRec* __restrict__ log,
+                                                         const uint32_t* __restrict__ log_cnt, int nlogs, int log_cap,
+                                                         Cand* __restrict__ cand, uint32_t* __restrict__ cand_cnt,
+                                                         int cap) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= nlogs) return;
+    const uint32_t n = log_cnt[w];
+    const HitRec* L = log + (int64_t)w * log_cap;
+    for (uint32_t i = lane; i < n; i += 32) {
+        int4 raw = __ldg(reinterpret_cast<const int4*>(L + i));
+        HitRec h = *reinterpret_cast<HitRec*>(&raw);
+        uint32_t pos = atomicAdd(cand_cnt + h.q, 1u);
+        if (pos < (uint32_t)cap) {
+            Cand c; c.score = h.score; c.row = h.row;
+            cand[(int64_t)h.q * cap + pos] = c;
+        }
     }
 }
 
@@ -342,6 +399,11 @@ int umma_init() {
     return TRX_OK;
 }
 
+int umma_grid(int64_t nq, int64_t n, int sm_count) {
+    int64_t units = ((nq + BM - 1) / BM) * ((n + BN - 1) / BN);
+    return (int)(units < sm_count ? units : sm_count);
+}
+
 int umma_num_slices(int64_t n) {
     int64_t NT = (n + BN - 1) / BN;
     return (int)(NT < 8 ? NT : 8);
@@ -360,13 +422,22 @@ int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st) {
     p.NT = (int)((a.n + BN - 1) / BN);
     p.S = a.mode == MODE_SLOTMAX ? umma_num_slices(a.n) : p.NT;
     p.out = a.out; p.out_ld = a.out_ld;
-    p.thr = a.thr; p.cand = a.cand; p.cand_cnt = a.cand_cnt; p.cap = a.cap;
+    p.thr = a.thr; p.cand_cnt = a.cand_cnt;
+    p.log = a.log; p.log_cnt = a.log_cnt; p.log_cap = a.log_cap;
     p.slots = a.out;  // SLOTMAX reuses `out` as the [nq][S][32] slot buffer
     int64_t units = (int64_t)p.MT * p.S;
     int grid = (int)(units < sm_count ? units : sm_count);
     switch (a.mode) {
         case MODE_STORE: return launch_mode<MODE_STORE>(mq, mx, p, grid, st);
-        case MODE_THRESH: return launch_mode<MODE_THRESH>(mq, mx, p, grid, st);
+        case MODE_THRESH: {
+            TRX_TRY(launch_mode<MODE_THRESH>(mq, mx, p, grid, st));
+            const int nlogs = grid * 128;
+            k2_scatter_kernel<<<(nlogs * 32 + 255) / 256, 256, 0, st>>>(a.log, a.log_cnt, nlogs, a.log_cap, a.cand,
+                                                                         a.cand_cnt, a.cap);
+            count_launch();
+            TRX_CUDA(cudaGetLastError());
+            return TRX_OK;
+        }
         case MODE_SLOTMAX: return launch_mode<MODE_SLOTMAX>(mq, mx, p, grid, st);
     }
     set_error("k2: bad mode %d", a.mode);

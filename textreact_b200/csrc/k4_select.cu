@@ -264,16 +264,19 @@ __global__ void __launch_bounds__(256) k4_rescore_kernel(RescoreArgs a) {
     __shared__ float s_qn2;
 
     const int64_t q = blockIdx.x;
+    const int64_t oq = a.qmap ? (int64_t)a.qmap[q] : q;   // caller-visible query index
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int k = a.k;
-    float* Dq = a.D + q * k;
-    int64_t* Iq = a.I + q * k;
+    float* Dq = a.D + oq * k;
+    int64_t* Iq = a.I + oq * k;
     const float fill = METRIC == TRX_METRIC_L2 ? FLT_MAX : -FLT_MAX;
 
     const uint32_t cnt_raw = a.cand_cnt[q];
     if (cnt_raw > (uint32_t)a.cap) {  // list overflowed: invariant lost
         if (threadIdx.x == 0) {
-            a.fb_list[atomicAdd(a.fb_count, 1u)] = (int32_t)q;
+            uint32_t slot = atomicAdd(a.fb_count, 1u);
+            a.fb_list[slot] = (int32_t)oq;
+            a.fb_thr[slot] = -INFINITY;
             atomicAdd((unsigned long long*)&a.counters[2], 1ull);
             atomicAdd((unsigned long long*)&a.counters[3], (unsigned long long)cnt_raw);
         }
@@ -314,9 +317,8 @@ __global__ void __launch_bounds__(256) k4_rescore_kernel(RescoreArgs a) {
     const bool complete = !(thr > -INFINITY);  // every eligible row is in the list
 
     int m_done = 0;
-    int m = k + (k / 4 > 16 ? k / 4 : 16);
-    m = (m + 7) & ~7;
-    if (m > n_valid) m = n_valid;
+    int m = (2 * k + 56 + 7) & ~7;   // first round sized so the certificate usually holds at once
+    if (m > n_valid || complete) m = n_valid;
     bool certified = false;
     for (;;) {
         for (int i = m_done + wid; i < m; i += nwarp) {
@@ -345,7 +347,10 @@ __global__ void __launch_bounds__(256) k4_rescore_kernel(RescoreArgs a) {
     }
     if (!certified) {
         if (threadIdx.x == 0) {
-            a.fb_list[atomicAdd(a.fb_count, 1u)] = (int32_t)q;
+            uint32_t slot = atomicAdd(a.fb_count, 1u);
+            a.fb_list[slot] = (int32_t)oq;
+            // every true top-k row scores at least the k-th best exact score seen so far
+            a.fb_thr[slot] = m >= k ? key_score(ekeys[k - 1]) - a.eps_acc[q] : -INFINITY;
             atomicAdd((unsigned long long*)&a.counters[1], 1ull);
         }
         return;

@@ -72,6 +72,10 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t*
     const int64_t s = list[blockIdx.x];
     for (int c = threadIdx.x; c < d; c += blockDim.x) dst[(int64_t)blockIdx.x * d + c] = src[s * d + c];
 }
+__global__ void add_bias_kernel(float* __restrict__ v, int n, float b) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += b;
+}
 __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ list, int n,
                                   int32_t* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,18 +100,22 @@ struct trx_index {
     // options
     int opt_path = TRX_PATH_AUTO;
     int max_batch = 8192;
-    int target = 512;       // expected candidates per query
+    int target = 768;       // expected candidates per query
     int sample_rate = 32;
     int stream_max_batch = 0;  // AUTO: batches <= this use the K3 streaming prefilter
     int timing = 0;
+    float thr_bias = 0.f;   // experiments only: added to every estimated threshold
     // workspaces (sized for max_batch)
     int ws_batch = 0, ws_cap = 0;
     float* q32 = nullptr; __nv_bfloat16* q16 = nullptr; float* qnorm2 = nullptr; float* eps = nullptr;
     float* thr = nullptr; int32_t* excl = nullptr;
     Cand* cand = nullptr; uint32_t* cand_cnt = nullptr;
     float* slots = nullptr; size_t slots_elems = 0;
+    HitRec* hitlog = nullptr; uint32_t* hitlog_cnt = nullptr; size_t hitlog_elems = 0; int hitlog_n = 0;
     float* Dd = nullptr; int64_t* Id = nullptr; int ws_k = 0;
     int32_t* fb_list = nullptr; uint32_t* fb_count = nullptr; uint64_t* counters = nullptr;
+    float* fb_thr = nullptr; float* eps_acc = nullptr; float* neg_inf = nullptr;
+    int32_t* fb_list2 = nullptr; float* thr2 = nullptr;   // second-chance (threshold-guided) lists
     float* qfb = nullptr; int32_t* exfb = nullptr;
     float* xscores = nullptr; size_t xscores_elems = 0;  // exact-path score rows
     cudaStream_t own_stream = nullptr;
@@ -119,6 +127,8 @@ static void free_ws(trx_index* ix) {
     dfree(ix->q32); dfree(ix->q16); dfree(ix->qnorm2); dfree(ix->eps); dfree(ix->thr); dfree(ix->excl);
     dfree(ix->cand); dfree(ix->cand_cnt); dfree(ix->slots); dfree(ix->Dd); dfree(ix->Id);
     dfree(ix->fb_list); dfree(ix->qfb); dfree(ix->exfb); dfree(ix->xscores);
+    dfree(ix->fb_thr); dfree(ix->eps_acc); dfree(ix->neg_inf); dfree(ix->fb_list2); dfree(ix->thr2);
+    dfree(ix->hitlog); dfree(ix->hitlog_cnt); ix->hitlog_elems = 0; ix->hitlog_n = 0;
     ix->ws_batch = ix->ws_cap = ix->ws_k = 0; ix->slots_elems = 0; ix->xscores_elems = 0;
 }
 
@@ -160,6 +170,7 @@ static int ensure_ws(trx_index* ix, int B, int k, int cap) {
         int nb = std::max(B, ix->ws_batch), nc = std::max(cap, ix->ws_cap);
         dfree(ix->q32); dfree(ix->q16); dfree(ix->qnorm2); dfree(ix->eps); dfree(ix->thr); dfree(ix->excl);
         dfree(ix->cand); dfree(ix->cand_cnt); dfree(ix->fb_list); dfree(ix->qfb); dfree(ix->exfb);
+        dfree(ix->fb_thr); dfree(ix->eps_acc); dfree(ix->neg_inf); dfree(ix->fb_list2); dfree(ix->thr2);
         dfree(ix->Dd); dfree(ix->Id); ix->ws_k = 0;
         TRX_TRY(dmalloc(&ix->q32, (size_t)nb * ix->d));
         TRX_TRY(dmalloc(&ix->q16, (size_t)nb * ix->Kp));
@@ -172,6 +183,15 @@ static int ensure_ws(trx_index* ix, int B, int k, int cap) {
         TRX_TRY(dmalloc(&ix->fb_list, (size_t)nb));
         TRX_TRY(dmalloc(&ix->qfb, (size_t)nb * ix->d));
         TRX_TRY(dmalloc(&ix->exfb, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->fb_thr, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->eps_acc, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->neg_inf, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->fb_list2, (size_t)nb));
+        TRX_TRY(dmalloc(&ix->thr2, (size_t)nb));
+        {
+            std::vector<float> ninf((size_t)nb, -INFINITY);
+            TRX_CUDA(cudaMemcpy(ix->neg_inf, ninf.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+        }
         ix->ws_batch = nb; ix->ws_cap = nc;
     }
     if (k > ix->ws_k) {
@@ -264,7 +284,7 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
     } else {
         TRX_TRY(ensure_sample(ix, st));
         TRX_TRY(launch_query_prep(qdev, B, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, st));
-        TRX_TRY(launch_eps(ix->qnorm2, ix->norm2_max, B, ix->d, ix->metric, ix->eps, st));
+        TRX_TRY(launch_eps(ix->qnorm2, ix->norm2_max, B, ix->d, ix->metric, ix->eps, ix->eps_acc, st));
         TRX_CUDA(cudaMemsetAsync(ix->cand_cnt, 0, (size_t)B * 4, st));
         TRX_CUDA(cudaMemsetAsync(ix->fb_count, 0, 4, st));
         const int T = std::max(ix->target, 4 * k);
@@ -279,9 +299,27 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
             u.mode = 2; u.out = ix->slots;
             TRX_TRY(launch_umma(u, ix->sm_count, st));
             TRX_TRY(launch_slot_thr(ix->slots, B, S, std::min(r, 32 * S), ix->thr, st));
+            if (ix->thr_bias != 0.f) {
+                add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(ix->thr, (int)B, ix->thr_bias);
+                count_launch();
+            }
             if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[1], st));
             u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
             u.thr = ix->thr; u.cand = ix->cand; u.cand_cnt = ix->cand_cnt; u.cap = cap;
+            {   // private hit logs: 3x the expected hits per epilogue thread, at least 256 entries
+                const int grid = umma_grid(B, N, ix->sm_count);
+                const int nlogs = grid * 128;
+                double expect = 1.15 * (double)B * (double)T / (double)nlogs;
+                int log_cap = std::max(256, (int)(3.0 * expect) + 64);
+                size_t need_l = (size_t)nlogs * log_cap;
+                if (need_l > ix->hitlog_elems || nlogs > ix->hitlog_n) {
+                    dfree(ix->hitlog); dfree(ix->hitlog_cnt);
+                    TRX_TRY(dmalloc(&ix->hitlog, need_l));
+                    TRX_TRY(dmalloc(&ix->hitlog_cnt, (size_t)nlogs));
+                    ix->hitlog_elems = need_l; ix->hitlog_n = nlogs;
+                }
+                u.log = ix->hitlog; u.log_cnt = ix->hitlog_cnt; u.log_cap = log_cap;
+            }
             TRX_TRY(launch_umma(u, ix->sm_count, st));
             if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[2], st));
         } else {
@@ -305,23 +343,80 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
         ra.x32 = ix->x32; ra.d = ix->d; ra.n = N; ra.q32 = qdev; ra.nq = B;
         ra.groups = ix->has_groups ? ix->groups : nullptr; ra.excl = exdev;
         ra.k = k; ra.metric = ix->metric; ra.id_offset = ix->id_offset;
-        ra.D = ix->Dd; ra.I = ix->Id; ra.fb_list = ix->fb_list; ra.fb_count = ix->fb_count; ra.counters = ix->counters;
+        ra.D = ix->Dd; ra.I = ix->Id; ra.fb_list = ix->fb_list; ra.fb_count = ix->fb_count;
+        ra.fb_thr = ix->fb_thr; ra.eps_acc = ix->eps_acc; ra.qmap = nullptr; ra.counters = ix->counters;
         TRX_TRY(launch_rescore(ra, st));
 
         uint32_t nfb = 0;
         TRX_CUDA(cudaMemcpyAsync(&nfb, ix->fb_count, 4, cudaMemcpyDeviceToHost, st));
         TRX_CUDA(cudaStreamSynchronize(st));
         if (nfb > 0) {
-            gather_rows_kernel<<<nfb, 128, 0, st>>>(qdev, ix->fb_list, ix->d, ix->qfb);
-            count_launch();
-            const int32_t* exfb = nullptr;
-            if (exdev) {
-                gather_i32_kernel<<<(nfb + 255) / 256, 256, 0, st>>>(exdev, ix->fb_list, (int)nfb, ix->exfb);
-                count_launch();
-                exfb = ix->exfb;
+            // Queries without a certificate.  Second chance, still exact: K4 left the k-th best exact
+            // score it saw; every true top-k row scores at least that, so one fp32 streaming pass
+            // that appends rows above it yields a short COMPLETE list, which K4 then finishes.
+            // Only queries with no usable bound (overflow / fewer than k candidates) take the
+            // generic scan + radix select.
+            std::vector<int32_t> h_list(nfb);
+            std::vector<float> h_thr(nfb);
+            TRX_CUDA(cudaMemcpyAsync(h_list.data(), ix->fb_list, (size_t)nfb * 4, cudaMemcpyDeviceToHost, st));
+            TRX_CUDA(cudaMemcpyAsync(h_thr.data(), ix->fb_thr, (size_t)nfb * 4, cudaMemcpyDeviceToHost, st));
+            TRX_CUDA(cudaStreamSynchronize(st));
+            std::vector<int32_t> lite, gen;
+            std::vector<float> lite_thr;
+            for (uint32_t i = 0; i < nfb; i++) {
+                if (h_thr[i] > -INFINITY) { lite.push_back(h_list[i]); lite_thr.push_back(h_thr[i]); }
+                else gen.push_back(h_list[i]);
             }
-            TRX_CUDA(cudaGetLastError());
-            TRX_TRY(run_exact(ix, ix->qfb, exfb, ix->fb_list, nfb, k, st));
+            if (!lite.empty()) {
+                const int nl = (int)lite.size();
+                TRX_CUDA(cudaMemcpyAsync(ix->fb_list2, lite.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+                TRX_CUDA(cudaMemcpyAsync(ix->thr2, lite_thr.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+                gather_rows_kernel<<<nl, 128, 0, st>>>(qdev, ix->fb_list2, ix->d, ix->qfb);
+                count_launch();
+                const int32_t* exfb = nullptr;
+                if (exdev) {
+                    gather_i32_kernel<<<(nl + 255) / 256, 256, 0, st>>>(exdev, ix->fb_list2, nl, ix->exfb);
+                    count_launch();
+                    exfb = ix->exfb;
+                }
+                TRX_CUDA(cudaGetLastError());
+                TRX_CUDA(cudaMemsetAsync(ix->cand_cnt, 0, (size_t)nl * 4, st));
+                TRX_CUDA(cudaMemsetAsync(ix->fb_count, 0, 4, st));
+                StreamArgs a{};
+                a.x = ix->x32; a.pitch = ix->d; a.n = N; a.d = ix->d;
+                a.q32 = ix->qfb; a.q_pitch = ix->d; a.nq = nl;
+                a.metric = ix->metric; a.bf16 = false; a.append = true;
+                a.thr = ix->thr2; a.cand = ix->cand; a.cand_cnt = ix->cand_cnt; a.cap = cap;
+                TRX_TRY(launch_stream(a, ix->sm_count, st));
+                RescoreArgs rb = ra;
+                rb.thr = ix->neg_inf;      // complete list: certified once everything is rescored
+                rb.q32 = ix->qfb; rb.nq = nl; rb.excl = exfb; rb.qmap = ix->fb_list2;
+                TRX_TRY(launch_rescore(rb, st));
+                uint32_t nfb2 = 0;
+                TRX_CUDA(cudaMemcpyAsync(&nfb2, ix->fb_count, 4, cudaMemcpyDeviceToHost, st));
+                TRX_CUDA(cudaStreamSynchronize(st));
+                if (nfb2 > 0) {
+                    size_t g0 = gen.size();
+                    gen.resize(g0 + nfb2);
+                    TRX_CUDA(cudaMemcpy(gen.data() + g0, ix->fb_list, (size_t)nfb2 * 4, cudaMemcpyDeviceToHost));
+                }
+                ix->st.queries_exact += nl - (int64_t)nfb2;
+            }
+            if (!gen.empty()) {
+                const int ng = (int)gen.size();
+                TRX_CUDA(cudaMemcpyAsync(ix->fb_list2, gen.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, st));
+                gather_rows_kernel<<<ng, 128, 0, st>>>(qdev, ix->fb_list2, ix->d, ix->qfb);
+                count_launch();
+                const int32_t* exfb = nullptr;
+                if (exdev) {
+                    gather_i32_kernel<<<(ng + 255) / 256, 256, 0, st>>>(exdev, ix->fb_list2, ng, ix->exfb);
+                    count_launch();
+                    exfb = ix->exfb;
+                }
+                TRX_CUDA(cudaGetLastError());
+                TRX_TRY(run_exact(ix, ix->qfb, exfb, ix->fb_list2, ng, k, st));
+                TRX_CUDA(cudaStreamSynchronize(st));   // `gen` (host) must outlive the async upload
+            }
         }
     }
     if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[3], st));
@@ -503,6 +598,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->stream_max_batch = (int)v;
     } else if (!strcmp(key, "timing")) {
         ix->timing = v != 0;
+    } else if (!strcmp(key, "thr_bias")) {
+        ix->thr_bias = (float)v;
     } else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
