@@ -215,7 +215,8 @@ def main():
         sidx = None
         local = trx.IndexFlatIP(D_MODEL, device=local_rank)
     local.reserve(hi - lo)
-    for key, env in (("target_candidates", "TRX_TARGET"), ("sample_rate", "TRX_SAMPLE_RATE"), ("path", "TRX_PATH"), ("thr_bias", "TRX_THR_BIAS")):
+    for key, env in (("target_candidates", "TRX_TARGET"), ("sample_rate", "TRX_SAMPLE_RATE"), ("path", "TRX_PATH"), ("thr_bias", "TRX_THR_BIAS"),
+                     ("umma_pair", "TRX_UMMA_PAIR")):
         if os.environ.get(env):          # tuning knobs for experiments; defaults are what is reported
             local.set_option(key, float(os.environ[env]))
     gen = torch.Generator(device=dev)

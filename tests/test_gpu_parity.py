@@ -41,13 +41,16 @@ def test_exact_path_small(metric, shape):
     assert st["queries_exact"] == nq
 
 
-def test_umma_raw_scores_match_bf16_matmul():
-    """K2 in STORE mode against torch: validates TMA swizzle, UMMA descriptors, TMEM readout."""
+@pytest.mark.parametrize("pair", [0, 1])
+def test_umma_raw_scores_match_bf16_matmul(pair):
+    """K2 in STORE mode against torch: validates TMA swizzle, UMMA descriptors, TMEM readout,
+    for the single-CTA (cta_group::1) and the CTA-pair (cta_group::2) tilings."""
     import torch
     trx = _engine()
     n, d, nq = 20000, 768, 300
     xb, xq = util.gaussian(n, d, 3), util.gaussian(nq, d, 4)
     idx = trx.IndexFlatIP(d)
+    idx.set_option("umma_pair", pair)
     idx.add(xb)
     got = idx.debug_scores_umma(torch.from_numpy(xq).cuda(), 256, n - 256 - 77).cpu().numpy()
     idx.close()
@@ -57,14 +60,14 @@ def test_umma_raw_scores_match_bf16_matmul():
 
 
 @pytest.mark.parametrize("metric", [IP, L2])
-@pytest.mark.parametrize("path_name", ["stream", "umma"])
+@pytest.mark.parametrize("path_name", ["stream", "umma", "umma_single_cta"])
 def test_prefilter_paths_gaussian(metric, path_name):
     trx = _engine()
-    path = {"stream": trx.PATH_STREAM, "umma": trx.PATH_UMMA}[path_name]
+    path = {"stream": trx.PATH_STREAM, "umma": trx.PATH_UMMA, "umma_single_cta": trx.PATH_UMMA}[path_name]
     n, d, k = 60000, 768, 20
     nq = 6 if path_name == "stream" else 300
     xb, xq = util.gaussian(n, d, 5), util.gaussian(nq, d, 6)
-    D, I, st = _run(xb, xq, k, metric, path)
+    D, I, st = _run(xb, xq, k, metric, path, umma_pair=0 if path_name == "umma_single_cta" else 1)
     oracle.check_parity(D, I, xb, xq, k, metric)
     assert st["last_path"] == path
     assert st["queries_exact"] <= nq // 10, st      # the certificate should hold for almost all

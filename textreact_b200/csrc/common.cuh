@@ -137,9 +137,10 @@ struct UmmaArgs {
     float* out; int64_t out_ld;
     const float* thr; Cand* cand; uint32_t* cand_cnt; int cap;
     HitRec* log; uint32_t* log_cnt; int log_cap;   // mode 1: [umma_grid*128][log_cap] private hit logs
+    bool pair;                                     // CTA-pair tiling (tcgen05 cta_group::2, 256-query tiles)
 };
 int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st);
-int umma_grid(int64_t nq, int64_t n, int sm_count);  // CTAs the THRESH pass will launch
+int umma_grid(int64_t nq, int64_t n, int sm_count, bool pair, bool slotmax);  // CTAs a launch will use
 int umma_init();  // resolves cuTensorMapEncodeTiled
 int umma_num_slices(int64_t n);  // S of the SLOTMAX mode (out = slots[nq][S][32])
 // r-th largest of the S*32 slot maxima of each query -> thr

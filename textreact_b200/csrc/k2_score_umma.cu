@@ -5,13 +5,20 @@
 // Replaces the `sgemm` + heap/reservoir inner loop of faiss `index.search`
 // (retrieve/retrieve_faiss.py:71) for batched queries.
 //
-//   D[128 queries x 256 corpus rows] (TMEM, fp32) += A[128 x 64] (smem, bf16) . B[256 x 64]^T
+// Two tilings of the same kernel (template parameter PAIR):
+//   PAIR = false  one CTA per tile: D[128 q x 256 rows] += A[128x64] . B[256x64]^T,
+//                 tcgen05.mma.cta_group::1, 4-stage 48 KB smem ring.
+//   PAIR = true   a CTA pair (cluster of 2, one TPC) per 256 q x 256 rows tile,
+//                 tcgen05.mma.cta_group::2 (M=256): each CTA stages its own 128 query rows and HALF of
+//                 the corpus tile (32 KB / stage -> 6 stages), the leader CTA issues the MMAs for both,
+//                 each CTA's TMEM receives its own 128 query rows x 256 columns.  Halves the corpus
+//                 bytes every SM pulls from L2 and deepens the pipeline.
 //
-// Roles (one CTA per SM, 256 threads):
-//   warp 0    TMA producer: cp.async.bulk.tensor into a 4-stage 128B-swizzled smem ring
-//   warp 1    MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16)
+// Roles (256 threads per CTA):
+//   warp 0    TMA producer: cp.async.bulk.tensor into the 128B-swizzled smem ring
+//   warp 1    MMA issuer (leader CTA only in PAIR mode): one elected lane issues tcgen05.mma (K=16 steps)
 //   warp 2    TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
-//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32, one query row per thread
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 (software pipelined), one query row per thread
 // Epilogue modes:
 //   STORE    fp32 scores to HBM (tests / profiling only)
 //   THRESH   compare against the per-query threshold; hits go to a per-thread private log in HBM with
@@ -26,17 +33,28 @@ namespace trx {
 
 namespace {
 
-constexpr int BM = 128;      // queries per tile   (UMMA M)
-constexpr int BN = 256;      // corpus rows per tile (UMMA N)
+constexpr int BM = 128;      // query rows per CTA (TMEM lanes)
+constexpr int BN = 256;      // corpus rows per tile (UMMA N, TMEM columns per accumulator)
 constexpr int BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 256;
+
+template <bool PAIR>
+struct Cfg {
+    static constexpr int STAGES = PAIR ? 6 : 4;
+    static constexpr int A_BYTES = BM * BK * 2;                      // 16 KB
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                // corpus rows THIS CTA stages
+    static constexpr int B_BYTES = B_ROWS * BK * 2;                  // 16 / 32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TX_BYTES = PAIR ? 2 * STAGE_BYTES : STAGE_BYTES;   // landing on the (leader's) full barrier
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TILE_M = PAIR ? 2 * BM : BM;                // query rows per work tile
+    static constexpr int UMMA_M = TILE_M;
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128/256
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                      ((uint32_t)(UMMA_M >> 4) << 24);
+};
 
 enum { MODE_STORE = 0, MODE_THRESH = 1, MODE_SLOTMAX = 2 };
 
@@ -47,6 +65,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -72,23 +99,57 @@ __device__ __forceinline__ bool elect_one() {
         "}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool PAIR>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    if (PAIR) {
+        // executed by both CTAs of the pair; the peer bit of the barrier address is cleared so the
+        // transaction bytes of both land on the LEADER's full barrier
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    }
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+template <bool PAIR>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if (PAIR) {  // arrive on the barrier at this offset in BOTH CTAs of the pair
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
 }
+template <bool PAIR>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    if (PAIR) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    }
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -113,13 +174,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct KParams {
     int64_t nq, n;
     int KB;          // k-blocks
-    int MT, NT, S;   // query tiles, row tiles, slices (S == NT for STORE/THRESH)
+    int MT, NT, S;   // query tiles (of TILE_M rows), row tiles, slices (S == NT for STORE/THRESH)
     float* out; int64_t out_ld;
     const float* thr; uint32_t* cand_cnt;
     HitRec* log; uint32_t* log_cnt; int log_cap;   // THRESH: [grid*128][log_cap] private hit logs
@@ -128,12 +187,14 @@ struct KParams {
 
 }  // namespace
 
-template <int MODE>
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, KParams p) {
+    using C = Cfg<PAIR>;
+    constexpr int STAGES = C::STAGES;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
     // barrier layout (8 bytes each): full[STAGES] empty[STAGES] tfull[2] tempty[2] ; then tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -145,6 +206,10 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // position in the CTA pair
+    const bool leader = rank == 0;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // tile-processing unit id
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
@@ -152,70 +217,79 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        // tempty: one arrival per epilogue warp of every CTA feeding this accumulator
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int total_units = p.MT * p.S;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA stages its own operands) =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            for (int u = worker; u < total_units; u += nworkers) {
                 const int mt = u % p.MT, sl = u / p.MT;
                 const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
                 for (int nt = nt0; nt < nt1; nt++) {
                     for (int kb = 0; kb < p.KB; kb++) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                        tma_load_2d(sa, &tmap_q, full_bar(stage), kb * BK, mt * BM);
-                        tma_load_2d(sa + A_BYTES, &tmap_x, full_bar(stage), kb * BK, nt * BN);
+                        if (leader) mbar_expect_tx(full_bar(stage), C::TX_BYTES);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                        tma_load_2d<PAIR>(sa, &tmap_q, full_bar(stage), kb * BK, mt * C::TILE_M + (int)rank * BM);
+                        tma_load_2d<PAIR>(sa + C::A_BYTES, &tmap_x, full_bar(stage), kb * BK,
+                                          nt * BN + (int)rank * C::B_ROWS);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        int stage = 0; uint32_t phase = 0;
-        int as = 0; uint32_t aphase = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-            const int sl = u / p.MT;
-            const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
-            for (int nt = nt0; nt < nt1; nt++) {
-                mbar_wait(tempty_bar(as), aphase ^ 1u);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < p.KB; kb++) {
-                    mbar_wait(full_bar(stage), phase);
+        // ===================== MMA issuer (leader CTA drives both tensor cores) =====================
+        if (leader) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int u = worker; u < total_units; u += nworkers) {
+                const int sl = u / p.MT;
+                const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
+                for (int nt = nt0; nt < nt1; nt++) {
+                    mbar_wait(tempty_bar(as), aphase ^ 1u);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                        const uint64_t adesc = make_smem_desc(sa);
-                        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                    for (int kb = 0; kb < p.KB; kb++) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                            const uint64_t adesc = make_smem_desc(sa);
+                            const uint64_t bdesc = make_smem_desc(sa + C::A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; k++) {
-                            // advance 16 elements = 32 bytes inside the 128-byte swizzle row
-                            tc_mma(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
-                                   (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < BK / UMMA_K; k++) {
+                                // advance 16 elements = 32 bytes inside the 128-byte swizzle row
+                                tc_mma<PAIR>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), C::IDESC,
+                                             (kb | k) != 0 ? 1u : 0u);
+                            }
+                            tc_commit<PAIR>(empty_bar(stage));                    // frees the smem slot(s) when the MMAs retire
+                            if (kb == p.KB - 1) tc_commit<PAIR>(tfull_bar(as));   // accumulator(s) ready
                         }
-                        tc_commit(empty_bar(stage));                      // frees the smem slot when the MMAs retire
-                        if (kb == p.KB - 1) tc_commit(tfull_bar(as));     // accumulator ready
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++as == 2) { as = 0; aphase ^= 1u; }
                 }
-                if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
     } else if (warp >= 4) {
@@ -225,10 +299,10 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int64_t log_id = (int64_t)blockIdx.x * 128 + (threadIdx.x - 128);
         HitRec* my_log = MODE == MODE_THRESH ? p.log + log_id * p.log_cap : nullptr;
         uint32_t nlog = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        for (int u = worker; u < total_units; u += nworkers) {
             const int mt = u % p.MT, sl = u / p.MT;
             const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
-            const int64_t row = (int64_t)mt * BM + wq * 32 + lane;  // query handled by this thread
+            const int64_t row = (int64_t)mt * C::TILE_M + rank * BM + wq * 32 + lane;  // query of this thread
             const bool row_ok = row < p.nq;
             float thr = INFINITY;
             if (MODE == MODE_THRESH && row_ok) thr = p.thr[row];
@@ -308,7 +382,11 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     if (ch + 2 < BN / 32) tc_ld32(tbase + (uint32_t)((ch + 2) * 32), va);
                     else {  // everything of this accumulator is in registers: hand TMEM back to the MMA warp
                         tc_fence_before();
-                        mbar_arrive(tempty_bar(as));
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (PAIR) mbar_arrive_cluster(tempty_bar(as), 0);   // the leader's barrier
+                            else mbar_arrive(tempty_bar(as));
+                        }
                     }
                     process(vb, ch + 1);
                 }
@@ -325,10 +403,11 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync(); else __syncthreads();   // PAIR: the peer may still target our barriers / TMEM
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -373,18 +452,62 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_r
     return TRX_OK;
 }
 
-template <int MODE>
+template <int MODE, bool PAIR>
 int launch_mode(const CUtensorMap& mq, const CUtensorMap& mx, const KParams& p, int grid, cudaStream_t st) {
-    auto kern = k2_umma_kernel<MODE>;
+    auto kern = k2_umma_kernel<MODE, PAIR>;
     static bool attr_done = false;
     if (!attr_done) {
-        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<PAIR>::SMEM_BYTES));
         attr_done = true;
     }
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mx, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<PAIR>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TRX_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mx, p));
     count_launch();
-    TRX_CUDA(cudaGetLastError());
     return TRX_OK;
+}
+
+template <bool PAIR>
+int launch_tiling(const UmmaArgs& a, int sm_count, cudaStream_t st) {
+    using C = Cfg<PAIR>;
+    CUtensorMap mq, mx;
+    TRX_TRY(make_map(&mq, a.q16, a.nq, a.Kp, BM));
+    TRX_TRY(make_map(&mx, a.x16, a.n, a.Kp, C::B_ROWS));
+    KParams p;
+    p.nq = a.nq; p.n = a.n; p.KB = a.Kp / BK;
+    p.MT = (int)((a.nq + C::TILE_M - 1) / C::TILE_M);
+    p.NT = (int)((a.n + BN - 1) / BN);
+    p.S = a.mode == MODE_SLOTMAX ? umma_num_slices(a.n) : p.NT;
+    p.out = a.out; p.out_ld = a.out_ld;
+    p.thr = a.thr; p.cand_cnt = a.cand_cnt;
+    p.log = a.log; p.log_cnt = a.log_cnt; p.log_cap = a.log_cap;
+    p.slots = a.out;  // SLOTMAX reuses `out` as the [nq][S][32] slot buffer
+    const int grid = umma_grid(a.nq, a.n, sm_count, PAIR, a.mode == MODE_SLOTMAX);
+    switch (a.mode) {
+        case MODE_STORE: return launch_mode<MODE_STORE, PAIR>(mq, mx, p, grid, st);
+        case MODE_THRESH: {
+            TRX_TRY((launch_mode<MODE_THRESH, PAIR>(mq, mx, p, grid, st)));
+            const int nlogs = grid * 128;
+            k2_scatter_kernel<<<(nlogs * 32 + 255) / 256, 256, 0, st>>>(a.log, a.log_cnt, nlogs, a.log_cap, a.cand,
+                                                                         a.cand_cnt, a.cap);
+            count_launch();
+            TRX_CUDA(cudaGetLastError());
+            return TRX_OK;
+        }
+        case MODE_SLOTMAX: return launch_mode<MODE_SLOTMAX, PAIR>(mq, mx, p, grid, st);
+    }
+    set_error("k2: bad mode %d", a.mode);
+    return TRX_EINVAL;
 }
 
 }  // namespace
@@ -399,49 +522,27 @@ int umma_init() {
     return TRX_OK;
 }
 
-int umma_grid(int64_t nq, int64_t n, int sm_count) {
-    int64_t units = ((nq + BM - 1) / BM) * ((n + BN - 1) / BN);
-    return (int)(units < sm_count ? units : sm_count);
-}
-
 int umma_num_slices(int64_t n) {
     int64_t NT = (n + BN - 1) / BN;
     return (int)(NT < 8 ? NT : 8);
+}
+
+// CTAs a launch uses: persistent, one CTA (or CTA pair) per SM, never more workers than work units.
+int umma_grid(int64_t nq, int64_t n, int sm_count, bool pair, bool slotmax) {
+    const int tile_m = pair ? 2 * BM : BM;
+    int64_t MT = (nq + tile_m - 1) / tile_m;
+    int64_t NT = (n + BN - 1) / BN;
+    int64_t units = MT * (slotmax ? umma_num_slices(n) : NT);
+    int64_t workers = pair ? sm_count / 2 : sm_count;
+    if (units < workers) workers = units;
+    return (int)(pair ? 2 * workers : workers);
 }
 
 int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st) {
     if (a.nq <= 0 || a.n <= 0) return TRX_OK;
     TRX_TRY(umma_init());
     if (a.Kp % BK) { set_error("k2: Kp=%d not a multiple of %d", a.Kp, BK); return TRX_EINVAL; }
-    CUtensorMap mq, mx;
-    TRX_TRY(make_map(&mq, a.q16, a.nq, a.Kp, BM));
-    TRX_TRY(make_map(&mx, a.x16, a.n, a.Kp, BN));
-    KParams p;
-    p.nq = a.nq; p.n = a.n; p.KB = a.Kp / BK;
-    p.MT = (int)((a.nq + BM - 1) / BM);
-    p.NT = (int)((a.n + BN - 1) / BN);
-    p.S = a.mode == MODE_SLOTMAX ? umma_num_slices(a.n) : p.NT;
-    p.out = a.out; p.out_ld = a.out_ld;
-    p.thr = a.thr; p.cand_cnt = a.cand_cnt;
-    p.log = a.log; p.log_cnt = a.log_cnt; p.log_cap = a.log_cap;
-    p.slots = a.out;  // SLOTMAX reuses `out` as the [nq][S][32] slot buffer
-    int64_t units = (int64_t)p.MT * p.S;
-    int grid = (int)(units < sm_count ? units : sm_count);
-    switch (a.mode) {
-        case MODE_STORE: return launch_mode<MODE_STORE>(mq, mx, p, grid, st);
-        case MODE_THRESH: {
-            TRX_TRY(launch_mode<MODE_THRESH>(mq, mx, p, grid, st));
-            const int nlogs = grid * 128;
-            k2_scatter_kernel<<<(nlogs * 32 + 255) / 256, 256, 0, st>>>(a.log, a.log_cnt, nlogs, a.log_cap, a.cand,
-                                                                         a.cand_cnt, a.cap);
-            count_launch();
-            TRX_CUDA(cudaGetLastError());
-            return TRX_OK;
-        }
-        case MODE_SLOTMAX: return launch_mode<MODE_SLOTMAX>(mq, mx, p, grid, st);
-    }
-    set_error("k2: bad mode %d", a.mode);
-    return TRX_EINVAL;
+    return a.pair ? launch_tiling<true>(a, sm_count, st) : launch_tiling<false>(a, sm_count, st);
 }
 
 }  // namespace trx

@@ -104,6 +104,7 @@ struct trx_index {
     int sample_rate = 32;
     int stream_max_batch = 0;  // AUTO: batches <= this use the K3 streaming prefilter
     int timing = 0;
+    int umma_pair = 1;      // use the CTA-pair (cta_group::2) tiling when the batch has > 128 queries
     float thr_bias = 0.f;   // experiments only: added to every estimated threshold
     // workspaces (sized for max_batch)
     int ws_batch = 0, ws_cap = 0;
@@ -296,6 +297,7 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
             if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
             UmmaArgs u{};
             u.q16 = ix->q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
+            u.pair = ix->umma_pair && B > 128;
             u.mode = 2; u.out = ix->slots;
             TRX_TRY(launch_umma(u, ix->sm_count, st));
             TRX_TRY(launch_slot_thr(ix->slots, B, S, std::min(r, 32 * S), ix->thr, st));
@@ -307,7 +309,7 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
             u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
             u.thr = ix->thr; u.cand = ix->cand; u.cand_cnt = ix->cand_cnt; u.cap = cap;
             {   // private hit logs: 3x the expected hits per epilogue thread, at least 256 entries
-                const int grid = umma_grid(B, N, ix->sm_count);
+                const int grid = umma_grid(B, N, ix->sm_count, u.pair, false);
                 const int nlogs = grid * 128;
                 double expect = 1.15 * (double)B * (double)T / (double)nlogs;
                 int log_cap = std::max(256, (int)(3.0 * expect) + 64);
@@ -600,6 +602,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->timing = v != 0;
     } else if (!strcmp(key, "thr_bias")) {
         ix->thr_bias = (float)v;
+    } else if (!strcmp(key, "umma_pair")) {
+        ix->umma_pair = v != 0;
     } else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
@@ -612,6 +616,7 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "sample_rate")) *v = ix->sample_rate;
     else if (!strcmp(key, "stream_max_batch")) *v = ix->stream_max_batch;
     else if (!strcmp(key, "timing")) *v = ix->timing;
+    else if (!strcmp(key, "umma_pair")) *v = ix->umma_pair;
     else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
@@ -649,6 +654,7 @@ int trx_debug_scores_umma(trx_index* ix, const float* xq, int64_t nq, int64_t ro
     UmmaArgs u{};
     u.q16 = ix->q16; u.nq = nq; u.x16 = ix->x16 + row0 * ix->Kp; u.n = n; u.Kp = ix->Kp;
     u.mode = 0; u.out = out; u.out_ld = n;
+    u.pair = ix->umma_pair && nq > 128;
     TRX_TRY(launch_umma(u, ix->sm_count, st));
     TRX_CUDA(cudaStreamSynchronize(st));
     return TRX_OK;
