@@ -1,0 +1,63 @@
+"""CPU: libtrx.so loads and exports every symbol include/trx.h declares; failures are reported
+through return codes and trx_last_error, never by aborting.  No compute happens here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "trx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(trx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for need in ("trx_create", "trx_add", "trx_search", "trx_set_groups", "trx_reset", "trx_destroy",
+                 "trx_last_error", "trx_stats", "trx_merge_topk"):
+        assert need in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from textreact_b200 import _lib
+    L = _lib.lib()
+    for s in declared_symbols():
+        assert hasattr(L, s), f"libtrx.so does not export {s}"
+    assert set(_lib.SIGNATURES) == set(declared_symbols())
+    assert b"sm_100a" in L.trx_version()
+
+
+def test_stats_struct_matches_header_layout():
+    from textreact_b200 import _lib
+    # 7 x int64, 2 x int32, int64, 2 x double
+    assert ctypes.sizeof(_lib.TrxStats) == 7 * 8 + 2 * 4 + 8 + 2 * 8
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import textreact_b200 as trx
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA device"):
+        trx.IndexFlatIP(8)
+    from textreact_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.trx_create(8, 0, 0, ctypes.byref(h)) == _lib.TRX_ENODEV
+    assert not h
+    assert L.trx_create(-1, 0, 0, ctypes.byref(h)) == _lib.TRX_EINVAL
+    assert b"dimension" in L.trx_last_error()
+    assert L.trx_search(None, None, 1, 1, None, None, None, None) == _lib.TRX_EINVAL
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "textreact_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("# oracle", ""), f"{f} mentions the oracle"

@@ -1,0 +1,101 @@
+"""CPU: the oracle (FAISS flat-search restatement) against the committed golden vectors and against
+itself (scalar path vs BLAS path vs float64 arbiter)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpu_flat as oracle
+from tests import util
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def load(path):
+    z = np.load(path)
+    g = z["groups"] if "groups" in z.files else None
+    e = z["excl"] if "excl" in z.files else None
+    return z["xb"], z["xq"], int(z["k"]), int(z["metric"]), g, e, z["D"], z["I"]
+
+
+def test_golden_files_present():
+    assert len(GOLDEN) >= 8
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("fn", ["seq", "blas"])
+def test_oracle_matches_golden(path, fn):
+    xb, xq, k, metric, g, e, D, I = load(path)
+    search = oracle.search_seq if fn == "seq" else oracle.search_blas
+    Do, Io = search(xb, xq, k, metric, g, e)
+    np.testing.assert_array_equal(Io, I)
+    np.testing.assert_allclose(Do, D, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_paths_agree_and_pass_parity_rule(metric):
+    xb, xq = util.gaussian(8000, 96, 1), util.gaussian(40, 96, 2)
+    D1, I1 = oracle.search_seq(xb, xq, 15, metric)
+    D2, I2 = oracle.search_blas(xb, xq, 15, metric, bs_q=16, bs_b=1000)   # odd blocking on purpose
+    r1 = oracle.check_parity(D1, I1, xb, xq, 15, metric)
+    r2 = oracle.check_parity(D2, I2, xb, xq, 15, metric)
+    assert r1["forced_ranks"] > 0 and r2["forced_ranks"] > 0
+    assert (I1 == I2).mean() > 0.99
+
+
+def test_dispatch_threshold_like_faiss():
+    xb = util.gaussian(500, 16, 3)
+    for nq in (1, 19, 20, 33):
+        xq = util.gaussian(nq, 16, 4)
+        D, I = oracle.search(xb, xq, 5)
+        oracle.check_parity(D, I, xb, xq, 5)
+
+
+def test_int_inputs_are_coerced_like_faiss_wrapper():
+    xb = util.fingerprints(300, 64, 5)             # int8, as morgan_fingerprint produces
+    xq = util.count_fingerprints(7, 64, 6)          # int64, as reaction_fingerprint_array produces
+    D, I = oracle.search_seq(xb, xq, 4, 1)
+    D2, I2 = oracle.search_seq(xb.astype(np.float32), xq.astype(np.float32), 4, 1)
+    np.testing.assert_array_equal(I, I2)
+    np.testing.assert_array_equal(D, D2)
+
+
+def test_ties_resolved_by_ascending_id():
+    xb = np.ones((10, 4), np.float32)
+    D, I = oracle.search_seq(xb, np.ones((2, 4), np.float32), 4, 0)
+    np.testing.assert_array_equal(I, [[0, 1, 2, 3]] * 2)
+    D, I = oracle.search_blas(xb, np.ones((25, 4), np.float32), 4, 1, bs_b=3)
+    np.testing.assert_array_equal(I, [[0, 1, 2, 3]] * 25)
+
+
+def test_padding_when_k_exceeds_rows():
+    xb, xq = util.gaussian(3, 8, 7), util.gaussian(2, 8, 8)
+    D, I = oracle.search_seq(xb, xq, 5, 0)
+    assert (I[:, 3:] == -1).all() and (D[:, 3:] == np.float32(-oracle.FLT_MAX)).all()
+    D, I = oracle.search_seq(xb, xq, 5, 1)
+    assert (I[:, 3:] == -1).all() and (D[:, 3:] == np.float32(oracle.FLT_MAX)).all()
+
+
+def test_mask_equals_post_filter():
+    """engine-side exclusion == the consumer filter of textreact/dataset.py:74-76 applied to a deeper list"""
+    n, g = 2000, 5
+    xb, xq = util.clustered_unit(n, 48, 9, ncent=20), util.clustered_unit(30, 48, 10, ncent=20)
+    groups = (np.arange(n) // g).astype(np.int32)
+    excl = groups[np.random.default_rng(11).integers(0, n, 30)].copy()
+    excl[::4] = -1
+    k = 10
+    D, I = oracle.search_seq(xb, xq, k, 0, groups, excl)
+    D2, I2 = oracle.search_seq(xb, xq, k + g, 0)
+    corpus_text = {j: f"text-{groups[j]}" for j in range(n)}        # one paragraph per group
+    for i in range(30):
+        gold = None if excl[i] < 0 else f"text-{excl[i]}"
+        ids = [j for j in I2[i].tolist() if gold is None or corpus_text[j] != gold][:k]
+        np.testing.assert_array_equal(I[i], ids)
+
+
+def test_post_filter_semantics():
+    corpus = {"a": "T1", "b": "T1", "c": "T2", "d": "T3"}
+    assert oracle.post_filter(["a", "zz", "b", "c", "d"], corpus) == ["a", "c", "d"]            # unknown id + dedup
+    assert oracle.post_filter(["a", "b", "c", "d"], corpus, gold_text="T1") == ["c", "d"]        # gold skip
+    assert oracle.post_filter(["a", "b", "c", "d"], corpus, gold_text="T2", num_neighbors=1) == ["a"]

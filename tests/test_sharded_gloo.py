@@ -1,0 +1,106 @@
+"""CPU, world_size 2, gloo: the host logic of the row-sharded search (shard bounds, global id offsets,
+all-gather plumbing, merge order).  The CUDA engine cannot run here, so the two seams of
+ShardedIndexFlat are filled with test doubles built on the oracle; the product defaults are untouched."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleLocalIndex:
+    """Stands in for textreact_b200.IndexFlat on a CPU box."""
+
+    def __init__(self, d, metric):
+        self.d, self.metric, self.xb, self.off, self.groups = d, metric, None, 0, None
+
+    @property
+    def ntotal(self):
+        return 0 if self.xb is None else self.xb.shape[0]
+
+    def add(self, x):
+        self.xb = np.ascontiguousarray(x, dtype=np.float32)
+
+    def set_id_offset(self, off):
+        self.off = off
+
+    def set_groups(self, g):
+        self.groups = np.ascontiguousarray(g, dtype=np.int32)
+
+    def search(self, xq, k, *, exclude=None):
+        from oracle import cpu_flat as oracle
+        D, I = oracle.search_seq(self.xb, xq, k, self.metric, self.groups, exclude)
+        return D, np.where(I >= 0, I + self.off, -1)
+
+
+def numpy_merge(Dg, Ig, metric):
+    """Reference merge: (score, id) order over the concatenated shard lists."""
+    Dg, Ig = Dg.numpy(), Ig.numpy()
+    G, nq, k = Dg.shape
+    D = np.empty((nq, k), np.float32)
+    I = np.empty((nq, k), np.int64)
+    for q in range(nq):
+        d, i = Dg[:, q].reshape(-1), Ig[:, q].reshape(-1)
+        key = np.where(i >= 0, -d if metric == 0 else d, np.inf)
+        order = np.lexsort((np.where(i >= 0, i, np.iinfo(np.int64).max), key))[:k]
+        D[q], I[q] = d[order], i[order]
+    return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def _worker(rank, world, port, metric, with_mask, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cpu_flat as oracle
+        from textreact_b200.sharded import ShardedIndexFlat, shard_bounds
+        rng = np.random.default_rng(5)
+        n, d, nq, k = 1001, 24, 9, 7                                  # odd n: uneven shards
+        xb = rng.standard_normal((n, d)).astype(np.float32)
+        xq = rng.standard_normal((nq, d)).astype(np.float32)
+        groups = (np.arange(n) // 4).astype(np.int32)
+        excl = groups[rng.integers(0, n, nq)].astype(np.int32) if with_mask else None
+        idx = ShardedIndexFlat(d, metric, local_factory=OracleLocalIndex, merge_fn=numpy_merge)
+        idx.add_global(xb)
+        lo, hi = shard_bounds(n, world, rank)
+        assert idx.local.ntotal == hi - lo and idx.ntotal == n
+        if with_mask:
+            idx.set_groups_global(groups)
+        D, I = idx.search(xq, k, exclude=excl)
+        Do, Io = oracle.search_seq(xb, xq, k, metric, groups if with_mask else None, excl)
+        np.testing.assert_array_equal(I, Io)
+        np.testing.assert_allclose(D, Do, rtol=1e-6)
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("metric,with_mask", [(0, False), (1, False), (0, True)])
+def test_two_rank_sharded_search_equals_unsharded(metric, with_mask):
+    world = 2
+    port = 29600 + os.getpid() % 300 + metric * 7 + int(with_mask)
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, metric, with_mask, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert len(out) == world
+
+
+def test_shard_bounds_cover_rows_exactly():
+    from textreact_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 1000, 16_000_000):
+        for w in (1, 2, 4, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1

@@ -64,8 +64,9 @@ class ShardedIndexFlat:
             D, I = torch.from_numpy(D), torch.from_numpy(I)
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
         Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-        dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+        # list-of-views form: accepted by NCCL (coalesced into one all-gather) and by gloo (CPU tests)
+        dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
+        dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
         Dm, Im = self._merge(Dg, Ig, self.metric_type)
         if as_numpy and isinstance(Dm, torch.Tensor):
             return Dm.cpu().numpy(), Im.cpu().numpy()
