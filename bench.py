@@ -169,7 +169,22 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def stage(msg):
+    """Progress line on stderr (rank-tagged): a stalled run shows where it stopped."""
+    if os.environ.get("TRX_BENCH_QUIET"):
+        return
+    print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - T_START:7.1f}s] {msg}",
+          file=sys.stderr, flush=True)
+
+
+T_START = time.perf_counter()
+
+
 def main():
+    import faulthandler
+    wd = float(os.environ.get("TRX_BENCH_WATCHDOG", "0"))
+    if wd > 0:   # dump every thread's stack and exit if the run is still alive after `wd` seconds
+        faulthandler.dump_traceback_later(wd, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -206,6 +221,7 @@ def main():
 
     rows, batch, name = workload(n_gpus, args)
     lo, hi = shard_bounds(rows, world, rank)
+    stage(f"process group up; shard rows [{lo}, {hi}) batch {batch}")
 
     # ---- corpus: dist G (iid N(0,1)), generated on the device per shard, seeded ------------------
     if world > 1:
@@ -234,6 +250,8 @@ def main():
         local.set_id_offset(lo)
         sidx._lo, sidx._ntotal_global = lo, rows
     index = sidx if sidx is not None else local
+    torch.cuda.synchronize()
+    stage("corpus resident")
 
     nb = args.steps + args.warmup
     qgen = torch.Generator(device=dev)
@@ -267,6 +285,8 @@ def main():
 
     for i in range(args.warmup):
         step_dev(i)
+        torch.cuda.synchronize()
+        stage(f"warm-up step {i} done")
     launches0 = local.stats()["launches"]
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -275,6 +295,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = local.stats()["launches"] - launches0
     qps = batch * args.steps / (ms * 1e-3)
+    stage(f"device-resident timing done: {ms / args.steps:.2f} ms/step")
 
     # ---- end to end through the public API with pinned host buffers -------------------------------
     hq = [torch.empty((batch, D_MODEL), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -301,6 +322,7 @@ def main():
     ms_e2e_dev = timed(step_e2e, args.steps)
     wall_e2e = time.perf_counter() - t0
     qps_e2e = batch * args.steps / (ms_e2e_dev * 1e-3)
+    stage(f"end-to-end timing done: {ms_e2e_dev / args.steps:.2f} ms/step")
 
     # ---- roofline of the dominant kernel (K2 main pass), CUDA events inside the library -----------
     local.set_option("timing", 1)

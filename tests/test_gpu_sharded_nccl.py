@@ -1,0 +1,66 @@
+"""GPU, world_size 2, NCCL: the row-sharded search on the real engine --
+local exact top-k per shard with global ids, all-gather over NVLink, device k-way merge (K5) --
+must equal the unsharded answer.  Skipped on a one-GPU box (the gloo test covers the host logic)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, metric, with_mask, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import cpu_flat as oracle
+        from tests import util
+        from textreact_b200.sharded import ShardedIndexFlat, shard_bounds
+        n, d, nq, k = 60001, 768, 300, 20                               # odd n: uneven shards
+        xb, xq = util.gaussian(n, d, 5), util.gaussian(nq, d, 6)
+        groups = (np.arange(n) // 4).astype(np.int32)
+        excl = groups[np.random.default_rng(7).integers(0, n, nq)].astype(np.int32) if with_mask else None
+        idx = ShardedIndexFlat(d, metric, device=rank)
+        idx.add_global(xb)
+        lo, hi = shard_bounds(n, world, rank)
+        assert idx.local.ntotal == hi - lo and idx.ntotal == n
+        if with_mask:
+            idx.set_groups_global(groups)
+        # device tensors in -> device tensors out, every rank holds the merged result
+        D, I = idx.search(torch.from_numpy(xq).cuda(), k,
+                          exclude=None if excl is None else torch.from_numpy(excl).cuda())
+        assert D.is_cuda and I.is_cuda
+        oracle.check_parity(D.cpu().numpy(), I.cpu().numpy(), xb, xq, k, metric,
+                            groups if with_mask else None, excl)
+        # host arrays in -> host arrays out
+        D2, I2 = idx.search(xq[:33], k, exclude=None if excl is None else excl[:33])
+        np.testing.assert_array_equal(I2, I.cpu().numpy()[:33])
+        out[rank] = idx.local.stats()["last_path"]
+        idx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("metric,with_mask", [(0, False), (1, False), (0, True)])
+def test_two_gpu_sharded_search_equals_unsharded(metric, with_mask):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    port = 29900 + os.getpid() % 300 + metric * 7 + int(with_mask)
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, metric, with_mask, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert len(out) == world

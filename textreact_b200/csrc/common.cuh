@@ -76,9 +76,12 @@ int launch_ingest(const float* x, int64_t n, int d, int Kp, int metric, __nv_bfl
 // One pseudo-randomly chosen row out of every `rate` consecutive rows -> xs16 [ns, Kp].
 int launch_sample_gather(const __nv_bfloat16* x16, int64_t n, int Kp, int rate, __nv_bfloat16* xs16,
                          int64_t ns, cudaStream_t st);
-// Queries: fp32 [B,d] -> bf16 [B,Kp] (L2: 2q and -1,-1,-1 in the norm columns) + |q|^2.
+// Start of a batch: queries fp32 [B,d] -> bf16 [B,Kp] (L2: 2q and -1,-1,-1 in the norm columns) + |q|^2;
+// when given (nullable as a group): certificate slack eps[q] = c * |q| * max|x| (IP; L2 doubles it and adds
+// norm slack) and the fp32 summation slack eps_acc[q]; cand_cnt[q] = 0; *fb_count = 0.
 int launch_query_prep(const float* q, int64_t B, int d, int Kp, int metric, __nv_bfloat16* q16,
-                      float* qnorm2, cudaStream_t st);
+                      float* qnorm2, const uint32_t* norm2_max_bits, float* eps, float* eps_acc,
+                      uint32_t* cand_cnt, uint32_t* fb_count, cudaStream_t st);
 
 // K3: CUDA-core streaming scorer.
 //   fp32 mode : exact scores (IP: q.x ; L2: -sum (q-x)^2), rows masked by group get -inf.
@@ -123,13 +126,9 @@ struct RescoreArgs {
 };
 int launch_rescore(const RescoreArgs& a, cudaStream_t st);
 
-// certificate slack: eps[q] = c * |q| * max|x| (IP) ; L2 doubles it and adds norm slack.
-int launch_eps(const float* qnorm2, const uint32_t* norm2_max_bits, int64_t nq, int d, int metric,
-               float* eps, float* eps_acc, cudaStream_t st);
-
 // K2: tcgen05 scoring GEMM.  A = queries bf16 [nq, Kp], B = rows bf16 [n, Kp].
 struct UmmaArgs {
-    const __nv_bfloat16* q16; int64_t nq;
+    const __nv_bfloat16* q16; int64_t nq;          // q16 must be allocated for round_up(nq, 8) rows
     const __nv_bfloat16* x16; int64_t n; int Kp;
     // mode 0: store fp32 scores out[q*out_ld + row]; mode 1: append candidates > thr[q];
     // mode 2: slot maxima -> out[(q*S + slice)*32 + slot]
@@ -142,8 +141,8 @@ struct UmmaArgs {
 int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st);
 int umma_grid(int64_t nq, int64_t n, int sm_count, bool pair, bool slotmax);  // CTAs a launch will use
 int umma_init();  // resolves cuTensorMapEncodeTiled
-int umma_num_slices(int64_t n);  // S of the SLOTMAX mode (out = slots[nq][S][32])
-// r-th largest of the S*32 slot maxima of each query -> thr
+int umma_num_slices(int64_t n, int64_t nq, int sm_count, bool pair);  // S of the SLOTMAX mode (out = slots[nq][S][32])
+// r-th largest of the S*32 slot maxima of each query -> thr (any S; S <= 8 stays in one warp's registers)
 int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st);
 
 // K5: merge G sorted lists per query.

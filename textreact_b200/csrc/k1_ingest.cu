@@ -118,13 +118,40 @@ int launch_sample_gather(const __nv_bfloat16* x16, int64_t n, int Kp, int rate, 
     return TRX_OK;
 }
 
+// Certificate slack (see DESIGN.md "exactness certificate").
+//   bf16 rounding: |q^.x^ - q.x| <= (2u + u^2) sum|q_i x_i| <= (2u+u^2) |q||x|, u = 2^-9
+//   fp32 accumulation (tensor core, prefilter) and fp32 rescore: each <= d * 2^-23 |q||x| (loose)
+//   IP : eps = (2^-8 * 1.002 + 2 d 2^-23) |q| max|x|
+//   L2 : prefilter score is 2 q.x - |x|^2  ->  2x the IP slack, + 2^-22 max|x|^2 for the 3-way norm
+//        split and + 2^-21 (|q|^2 + max|x|^2) for the fp32 evaluation of |q|^2 - sum (q-x)^2.
+__device__ __forceinline__ void certificate_slack(float qn2, float xm2, int d, int metric, float& eps, float& eps_acc) {
+    float qn = sqrtf(qn2) * 1.000001f, xn = sqrtf(xm2) * 1.000001f;
+    float cacc = 2.f * (float)(d + 3) * 1.1920929e-7f;
+    float c = 0.00390625f * 1.002f + cacc;
+    float e = c * qn * xn, ea = cacc * qn * xn;
+    if (metric == TRX_METRIC_L2) {
+        float extra = 2.4e-7f * xm2 + 4.8e-7f * (qn2 + xm2);
+        e = 2.f * e + extra;
+        ea = cacc * (qn2 + xm2) * 2.f + extra;  // sum (q-x)^2 <= 2(|q|^2+|x|^2)
+    }
+    eps = e * 1.0001f + 1e-37f;
+    eps_acc = ea * 1.0001f + 1e-37f;   // two fp32 evaluations of the same score differ by at most this
+}
+
+// Start of a batch, one launch: queries fp32 -> bf16 (+|q|^2), certificate slack, and the per-batch
+// counters (candidate counts, fallback count) zeroed.
 __global__ void __launch_bounds__(256) k1_query_prep_kernel(const float* __restrict__ q, int64_t B, int d, int Kp,
                                                             int metric, __nv_bfloat16* __restrict__ q16,
-                                                            float* __restrict__ qnorm2) {
+                                                            float* __restrict__ qnorm2,
+                                                            const uint32_t* __restrict__ norm2_max_bits,
+                                                            float* __restrict__ eps, float* __restrict__ eps_acc,
+                                                            uint32_t* __restrict__ cand_cnt,
+                                                            uint32_t* __restrict__ fb_count) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float scale = metric == TRX_METRIC_L2 ? 2.f : 1.f;  // exact in bf16
+    if (fb_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0u;
     for (int64_t r = warp0; r < B; r += nwarps) {
         const float* qr = q + r * (int64_t)d;
         __nv_bfloat16* yr = q16 + r * (int64_t)Kp;
@@ -137,49 +164,26 @@ __global__ void __launch_bounds__(256) k1_query_prep_kernel(const float* __restr
         for (int c = d + lane; c < Kp; c += 32)
             yr[c] = __float2bfloat16_rn((metric == TRX_METRIC_L2 && c < d + 3) ? -1.f : 0.f);
         acc = warp_sum(acc);
-        if (lane == 0) qnorm2[r] = acc;
+        if (lane == 0) {
+            qnorm2[r] = acc;
+            if (eps != nullptr) {
+                float e, ea;
+                certificate_slack(acc, __uint_as_float(*norm2_max_bits), d, metric, e, ea);
+                eps[r] = e; eps_acc[r] = ea;
+            }
+            if (cand_cnt != nullptr) cand_cnt[r] = 0u;
+        }
     }
 }
 
 int launch_query_prep(const float* q, int64_t B, int d, int Kp, int metric, __nv_bfloat16* q16, float* qnorm2,
-                      cudaStream_t st) {
+                      const uint32_t* norm2_max_bits, float* eps, float* eps_acc, uint32_t* cand_cnt,
+                      uint32_t* fb_count, cudaStream_t st) {
     if (B <= 0) return TRX_OK;
     int64_t blocks = (B + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k1_query_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, B, d, Kp, metric, q16, qnorm2);
-    count_launch();
-    TRX_CUDA(cudaGetLastError());
-    return TRX_OK;
-}
-
-// Certificate slack (see DESIGN.md "exactness certificate").
-//   bf16 rounding: |q^.x^ - q.x| <= (2u + u^2) sum|q_i x_i| <= (2u+u^2) |q||x|, u = 2^-9
-//   fp32 accumulation (tensor core, prefilter) and fp32 rescore: each <= d * 2^-23 |q||x| (loose)
-//   IP : eps = (2^-8 * 1.002 + 2 d 2^-23) |q| max|x|
-//   L2 : prefilter score is 2 q.x - |x|^2  ->  2x the IP slack, + 2^-22 max|x|^2 for the 3-way norm
-//        split and + 2^-21 (|q|^2 + max|x|^2) for the fp32 evaluation of |q|^2 - sum (q-x)^2.
-__global__ void k1_eps_kernel(const float* __restrict__ qnorm2, const uint32_t* __restrict__ norm2_max_bits,
-                              int64_t nq, int d, int metric, float* __restrict__ eps, float* __restrict__ eps_acc) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    float xm2 = __uint_as_float(*norm2_max_bits);
-    float qn = sqrtf(qnorm2[i]) * 1.000001f, xn = sqrtf(xm2) * 1.000001f;
-    float cacc = 2.f * (float)(d + 3) * 1.1920929e-7f;
-    float c = 0.00390625f * 1.002f + cacc;
-    float e = c * qn * xn, ea = cacc * qn * xn;
-    if (metric == TRX_METRIC_L2) {
-        float extra = 2.4e-7f * xm2 + 4.8e-7f * (qnorm2[i] + xm2);
-        e = 2.f * e + extra;
-        ea = cacc * (qnorm2[i] + xm2) * 2.f + extra;  // sum (q-x)^2 <= 2(|q|^2+|x|^2)
-    }
-    eps[i] = e * 1.0001f + 1e-37f;
-    eps_acc[i] = ea * 1.0001f + 1e-37f;   // two fp32 evaluations of the same score differ by at most this
-}
-
-int launch_eps(const float* qnorm2, const uint32_t* norm2_max_bits, int64_t nq, int d, int metric, float* eps,
-               float* eps_acc, cudaStream_t st) {
-    if (nq <= 0) return TRX_OK;
-    k1_eps_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(qnorm2, norm2_max_bits, nq, d, metric, eps, eps_acc);
+    k1_query_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, B, d, Kp, metric, q16, qnorm2, norm2_max_bits, eps,
+                                                           eps_acc, cand_cnt, fb_count);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;

@@ -5,15 +5,25 @@
 // Replaces the `sgemm` + heap/reservoir inner loop of faiss `index.search`
 // (retrieve/retrieve_faiss.py:71) for batched queries.
 //
-// Two tilings of the same kernel (template parameter PAIR):
+// Three tilings of the same kernel (template parameters PAIR, AR):
 //   PAIR = false  one CTA per tile: D[128 q x 256 rows] += A[128x64] . B[256x64]^T,
-//                 tcgen05.mma.cta_group::1, 4-stage 48 KB smem ring.
+//                 tcgen05.mma.cta_group::1.
+//                 AR = 128: 4-stage 48 KB smem ring (33..128 queries per tile)
+//                 AR = 32 : the small-batch variant (<= 32 queries): the A slot of a stage is 4 KB, so the
+//                           ring holds 6 stages = 192 KB of corpus in flight per SM -- this regime is
+//                           HBM-bound and bytes in flight are what buys bandwidth.  The MMA still has
+//                           M = 128; lanes >= 32 multiply whatever follows in the stage and are ignored.
+//                 In both, TMA only moves the query rows that exist (box of round8(nq) rows) when the
+//                 batch is a single tile: no out-of-bounds zero fill, less L2->smem traffic.
 //   PAIR = true   a CTA pair (cluster of 2, one TPC) per 256 q x 256 rows tile,
 //                 tcgen05.mma.cta_group::2 (M=256): each CTA stages its own 128 query rows and HALF of
 //                 the corpus tile (32 KB / stage -> 6 stages), the leader CTA issues the MMAs for both,
 //                 each CTA's TMEM receives its own 128 query rows x 256 columns.  Halves the corpus
 //                 bytes every SM pulls from L2 and deepens the pipeline.
 //
+// Work order (STORE/THRESH): corpus-tile major per worker -- worker w owns corpus tiles w, w+W, ... and runs
+// every query tile against each before moving on, so a corpus tile is fetched from HBM once (by one SM /
+// SM pair) and re-read from L2 for the other query tiles: DRAM traffic == one pass over the bf16 corpus.
 // Roles (256 threads per CTA):
 //   warp 0    TMA producer: cp.async.bulk.tensor into the 128B-swizzled smem ring
 //   warp 1    MMA issuer (leader CTA only in PAIR mode): one elected lane issues tcgen05.mma (K=16 steps)
@@ -40,14 +50,15 @@ constexpr int UMMA_K = 16;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 256;
 
-template <bool PAIR>
+template <bool PAIR, int AR>
 struct Cfg {
-    static constexpr int STAGES = PAIR ? 6 : 4;
-    static constexpr int A_BYTES = BM * BK * 2;                      // 16 KB
+    static_assert(AR == 128 || (AR == 32 && !PAIR), "A slot: 128 rows, or 32 for the small-batch single-CTA variant");
+    static constexpr int STAGES = (PAIR || AR == 32) ? 6 : 4;
+    static constexpr int A_BYTES = AR * BK * 2;                      // 16 KB (4 KB when AR == 32)
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                // corpus rows THIS CTA stages
     static constexpr int B_BYTES = B_ROWS * BK * 2;                  // 16 / 32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TX_BYTES = PAIR ? 2 * STAGE_BYTES : STAGE_BYTES;   // landing on the (leader's) full barrier
+    static constexpr int TX_SCALE = PAIR ? 2 : 1;                    // both CTAs' bytes land on the leader's full barrier
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int TILE_M = PAIR ? 2 * BM : BM;                // query rows per work tile
     static constexpr int UMMA_M = TILE_M;
@@ -178,19 +189,46 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 struct KParams {
     int64_t nq, n;
     int KB;          // k-blocks
-    int MT, NT, S;   // query tiles (of TILE_M rows), row tiles, slices (S == NT for STORE/THRESH)
+    int MT, NT, S;   // query tiles (of TILE_M rows), row tiles, slices (SLOTMAX only)
+    int a_box;       // query rows one A load moves (TMA box rows), <= AR
     float* out; int64_t out_ld;
     const float* thr; uint32_t* cand_cnt;
     HitRec* log; uint32_t* log_cnt; int log_cap;   // THRESH: [grid*128][log_cap] private hit logs
     float* slots;    // SLOTMAX: [nq][S][32]
 };
 
+// Work units of one worker (CTA or CTA pair), identical for the three roles.
+//   SLOTMAX      unit = (query tile, slice of consecutive corpus tiles), round-robin over workers
+//   STORE/THRESH unit = (corpus tile, query tile), corpus-tile major per worker (see header)
+struct Sched {
+    int MT, NT, S, W, w, R, rem;
+    bool slotmax;
+    __device__ __forceinline__ Sched(const KParams& p, int worker, int nworkers, bool sm)
+        : MT(p.MT), NT(p.NT), S(p.S), W(nworkers), w(worker), R(p.NT / nworkers), rem(p.NT % nworkers), slotmax(sm) {}
+    __device__ __forceinline__ int count() const {
+        if (slotmax) { const int u = MT * S; return u > w ? (u - w + W - 1) / W : 0; }
+        const int tail = rem * MT;
+        return R * MT + (tail > w ? (tail - w + W - 1) / W : 0);
+    }
+    __device__ __forceinline__ void get(int i, int& mt, int& nt0, int& nt1, int& sl) const {
+        if (slotmax) {
+            const int u = w + i * W;
+            mt = u % MT; sl = u / MT;
+            nt0 = (int)((int64_t)sl * NT / S); nt1 = (int)((int64_t)(sl + 1) * NT / S);
+        } else {
+            if (i < R * MT) { const int r = i / MT; mt = i - r * MT; nt0 = r * W + w; }
+            else { const int j = w + (i - R * MT) * W; const int t = j / MT; mt = j - t * MT; nt0 = R * W + t; }
+            nt1 = nt0 + 1; sl = nt0;
+        }
+    }
+};
+
 }  // namespace
 
-template <int MODE, bool PAIR>
+template <int MODE, bool PAIR, int AR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x, KParams p) {
-    using C = Cfg<PAIR>;
+    using C = Cfg<PAIR, AR>;
     constexpr int STAGES = C::STAGES;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -235,19 +273,21 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int total_units = p.MT * p.S;
+    const Sched sched(p, worker, nworkers, MODE == MODE_SLOTMAX);
+    const int my_units = sched.count();
+    const uint32_t tx_bytes = (uint32_t)(C::TX_SCALE * (p.a_box * BK * 2 + C::B_BYTES));
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA stages its own operands) =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int u = worker; u < total_units; u += nworkers) {
-                const int mt = u % p.MT, sl = u / p.MT;
-                const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
+            for (int ui = 0; ui < my_units; ui++) {
+                int mt, nt0, nt1, sl;
+                sched.get(ui, mt, nt0, nt1, sl);
                 for (int nt = nt0; nt < nt1; nt++) {
                     for (int kb = 0; kb < p.KB; kb++) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        if (leader) mbar_expect_tx(full_bar(stage), C::TX_BYTES);
+                        if (leader) mbar_expect_tx(full_bar(stage), tx_bytes);
                         const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                         tma_load_2d<PAIR>(sa, &tmap_q, full_bar(stage), kb * BK, mt * C::TILE_M + (int)rank * BM);
                         tma_load_2d<PAIR>(sa + C::A_BYTES, &tmap_x, full_bar(stage), kb * BK,
@@ -262,9 +302,9 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (leader) {
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int u = worker; u < total_units; u += nworkers) {
-                const int sl = u / p.MT;
-                const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
+            for (int ui = 0; ui < my_units; ui++) {
+                int mt, nt0, nt1, sl;
+                sched.get(ui, mt, nt0, nt1, sl);
                 for (int nt = nt0; nt < nt1; nt++) {
                     mbar_wait(tempty_bar(as), aphase ^ 1u);
                     tc_fence_after();
@@ -299,13 +339,30 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int64_t log_id = (int64_t)blockIdx.x * 128 + (threadIdx.x - 128);
         HitRec* my_log = MODE == MODE_THRESH ? p.log + log_id * p.log_cap : nullptr;
         uint32_t nlog = 0;
-        for (int u = worker; u < total_units; u += nworkers) {
-            const int mt = u % p.MT, sl = u / p.MT;
-            const int nt0 = (int)((int64_t)sl * p.NT / p.S), nt1 = (int)((int64_t)(sl + 1) * p.NT / p.S);
-            const int64_t row = (int64_t)mt * C::TILE_M + rank * BM + wq * 32 + lane;  // query of this thread
+        // threshold of the NEXT unit's query row is fetched one unit ahead (the query tile changes every unit)
+        auto row_of = [&](int mt) { return (int64_t)mt * C::TILE_M + rank * BM + wq * 32 + lane; };
+        float thr_next = INFINITY;
+        if (MODE == MODE_THRESH && my_units > 0) {
+            int mt, a, b, c;
+            sched.get(0, mt, a, b, c);
+            if (row_of(mt) < p.nq) thr_next = p.thr[row_of(mt)];
+        }
+        for (int ui = 0; ui < my_units; ui++) {
+            int mt, nt0, nt1, sl;
+            sched.get(ui, mt, nt0, nt1, sl);
+            const int64_t row = row_of(mt);  // query of this thread
             const bool row_ok = row < p.nq;
-            float thr = INFINITY;
-            if (MODE == MODE_THRESH && row_ok) thr = p.thr[row];
+            const float thr = thr_next;
+            if (MODE == MODE_THRESH) {
+                thr_next = INFINITY;
+                if (ui + 1 < my_units) {
+                    int mt2, a, b, c;
+                    sched.get(ui + 1, mt2, a, b, c);
+                    if (row_of(mt2) < p.nq) thr_next = p.thr[row_of(mt2)];
+                }
+            }
+            // a warp whose 32 query rows do not exist only hands the accumulator back
+            const bool warp_idle = (int64_t)mt * C::TILE_M + rank * BM + wq * 32 >= p.nq;
             float slot[32];
             if (MODE == MODE_SLOTMAX) {
 #pragma unroll
@@ -314,6 +371,16 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int nt = nt0; nt < nt1; nt++) {
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
+                if (warp_idle) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(tempty_bar(as), 0);
+                        else mbar_arrive(tempty_bar(as));
+                    }
+                    if (++as == 2) { as = 0; aphase ^= 1u; }
+                    continue;
+                }
                 const int64_t col0 = (int64_t)nt * BN;
                 const bool full_tile = col0 + BN <= p.n;
                 const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN);
@@ -411,8 +478,9 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
 }
 
-// One warp per private log: entries -> per-query candidate lists (the only global atomics of the
-// batched path, ~800 per query, issued with full-chip parallelism instead of from the epilogue).
+// One warp per private log: entries -> per-query candidate lists.  The entries of one log come from one
+// epilogue thread, i.e. from few distinct queries (one, for a single-tile batch), so the 32 entries a warp
+// handles per step are aggregated by query first: one global atomic per distinct query per step.
 __global__ void __launch_bounds__(256) k2_scatter_kernel(const HitRec* __restrict__ log,
                                                          const uint32_t* __restrict__ log_cnt, int nlogs, int log_cap,
                                                          Cand* __restrict__ cand, uint32_t* __restrict__ cand_cnt,
@@ -422,10 +490,19 @@ __global__ void __launch_bounds__(256) k2_scatter_kernel(const HitRec* __restric
     if (w >= nlogs) return;
     const uint32_t n = log_cnt[w];
     const HitRec* L = log + (int64_t)w * log_cap;
-    for (uint32_t i = lane; i < n; i += 32) {
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool have = i < n;
+        const uint32_t active = __ballot_sync(0xffffffffu, have);
+        if (!have) continue;
         int4 raw = __ldg(reinterpret_cast<const int4*>(L + i));
         HitRec h = *reinterpret_cast<HitRec*>(&raw);
-        uint32_t pos = atomicAdd(cand_cnt + h.q, 1u);
+        const uint32_t peers = __match_any_sync(active, h.q);
+        const int lead = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == lead) base = atomicAdd(cand_cnt + h.q, (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, lead);
+        const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
         if (pos < (uint32_t)cap) {
             Cand c; c.score = h.score; c.row = h.row;
             cand[(int64_t)h.q * cap + pos] = c;
@@ -452,18 +529,19 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_r
     return TRX_OK;
 }
 
-template <int MODE, bool PAIR>
+template <int MODE, bool PAIR, int AR>
 int launch_mode(const CUtensorMap& mq, const CUtensorMap& mx, const KParams& p, int grid, cudaStream_t st) {
-    auto kern = k2_umma_kernel<MODE, PAIR>;
+    auto kern = k2_umma_kernel<MODE, PAIR, AR>;
+    using C = Cfg<PAIR, AR>;
     static bool attr_done = false;
     if (!attr_done) {
-        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<PAIR>::SMEM_BYTES));
+        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg<PAIR>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -477,26 +555,30 @@ int launch_mode(const CUtensorMap& mq, const CUtensorMap& mx, const KParams& p, 
     return TRX_OK;
 }
 
-template <bool PAIR>
+template <bool PAIR, int AR>
 int launch_tiling(const UmmaArgs& a, int sm_count, cudaStream_t st) {
-    using C = Cfg<PAIR>;
-    CUtensorMap mq, mx;
-    TRX_TRY(make_map(&mq, a.q16, a.nq, a.Kp, BM));
-    TRX_TRY(make_map(&mx, a.x16, a.n, a.Kp, C::B_ROWS));
+    using C = Cfg<PAIR, AR>;
     KParams p;
     p.nq = a.nq; p.n = a.n; p.KB = a.Kp / BK;
     p.MT = (int)((a.nq + C::TILE_M - 1) / C::TILE_M);
     p.NT = (int)((a.n + BN - 1) / BN);
-    p.S = a.mode == MODE_SLOTMAX ? umma_num_slices(a.n) : p.NT;
+    p.S = a.mode == MODE_SLOTMAX ? umma_num_slices(a.n, a.nq, sm_count, PAIR) : p.NT;
+    // a batch that is a single query tile moves only the rows that exist (the caller allocates q16 for
+    // round8(nq) rows): no TMA out-of-bounds fill.  Several tiles: full boxes, the tail tile zero-filled.
+    const int64_t nq8 = (a.nq + 7) / 8 * 8;
+    p.a_box = (!PAIR && p.MT == 1) ? (int)(nq8 < AR ? nq8 : AR) : BM;
+    CUtensorMap mq, mx;
+    TRX_TRY(make_map(&mq, a.q16, (!PAIR && p.MT == 1) ? nq8 : a.nq, a.Kp, p.a_box));
+    TRX_TRY(make_map(&mx, a.x16, a.n, a.Kp, C::B_ROWS));
     p.out = a.out; p.out_ld = a.out_ld;
     p.thr = a.thr; p.cand_cnt = a.cand_cnt;
     p.log = a.log; p.log_cnt = a.log_cnt; p.log_cap = a.log_cap;
     p.slots = a.out;  // SLOTMAX reuses `out` as the [nq][S][32] slot buffer
     const int grid = umma_grid(a.nq, a.n, sm_count, PAIR, a.mode == MODE_SLOTMAX);
     switch (a.mode) {
-        case MODE_STORE: return launch_mode<MODE_STORE, PAIR>(mq, mx, p, grid, st);
+        case MODE_STORE: return launch_mode<MODE_STORE, PAIR, AR>(mq, mx, p, grid, st);
         case MODE_THRESH: {
-            TRX_TRY((launch_mode<MODE_THRESH, PAIR>(mq, mx, p, grid, st)));
+            TRX_TRY((launch_mode<MODE_THRESH, PAIR, AR>(mq, mx, p, grid, st)));
             const int nlogs = grid * 128;
             k2_scatter_kernel<<<(nlogs * 32 + 255) / 256, 256, 0, st>>>(a.log, a.log_cnt, nlogs, a.log_cap, a.cand,
                                                                          a.cand_cnt, a.cap);
@@ -504,7 +586,7 @@ int launch_tiling(const UmmaArgs& a, int sm_count, cudaStream_t st) {
             TRX_CUDA(cudaGetLastError());
             return TRX_OK;
         }
-        case MODE_SLOTMAX: return launch_mode<MODE_SLOTMAX, PAIR>(mq, mx, p, grid, st);
+        case MODE_SLOTMAX: return launch_mode<MODE_SLOTMAX, PAIR, AR>(mq, mx, p, grid, st);
     }
     set_error("k2: bad mode %d", a.mode);
     return TRX_EINVAL;
@@ -522,9 +604,16 @@ int umma_init() {
     return TRX_OK;
 }
 
-int umma_num_slices(int64_t n) {
-    int64_t NT = (n + BN - 1) / BN;
-    return (int)(NT < 8 ? NT : 8);
+// SLOTMAX slices per query tile: enough (query tile, slice) units to occupy every worker, at least 8.
+int umma_num_slices(int64_t n, int64_t nq, int sm_count, bool pair) {
+    const int tile_m = pair ? 2 * BM : BM;
+    const int64_t MT = (nq + tile_m - 1) / tile_m;
+    const int64_t NT = (n + BN - 1) / BN;
+    const int64_t workers = pair ? sm_count / 2 : sm_count;
+    int64_t S = (workers + MT - 1) / MT;
+    if (S < 8) S = 8;
+    if (S > 256) S = 256;
+    return (int)(NT < S ? NT : S);
 }
 
 // CTAs a launch uses: persistent, one CTA (or CTA pair) per SM, never more workers than work units.
@@ -532,7 +621,7 @@ int umma_grid(int64_t nq, int64_t n, int sm_count, bool pair, bool slotmax) {
     const int tile_m = pair ? 2 * BM : BM;
     int64_t MT = (nq + tile_m - 1) / tile_m;
     int64_t NT = (n + BN - 1) / BN;
-    int64_t units = MT * (slotmax ? umma_num_slices(n) : NT);
+    int64_t units = MT * (slotmax ? umma_num_slices(n, nq, sm_count, pair) : NT);
     int64_t workers = pair ? sm_count / 2 : sm_count;
     if (units < workers) workers = units;
     return (int)(pair ? 2 * workers : workers);
@@ -542,7 +631,8 @@ int launch_umma(const UmmaArgs& a, int sm_count, cudaStream_t st) {
     if (a.nq <= 0 || a.n <= 0) return TRX_OK;
     TRX_TRY(umma_init());
     if (a.Kp % BK) { set_error("k2: Kp=%d not a multiple of %d", a.Kp, BK); return TRX_EINVAL; }
-    return a.pair ? launch_tiling<true>(a, sm_count, st) : launch_tiling<false>(a, sm_count, st);
+    if (a.pair) return launch_tiling<true, 128>(a, sm_count, st);
+    return a.nq <= 32 ? launch_tiling<false, 32>(a, sm_count, st) : launch_tiling<false, 128>(a, sm_count, st);
 }
 
 }  // namespace trx

@@ -217,7 +217,8 @@ int launch_exact_topk(const float* s, int64_t ld, int64_t n, int64_t nq, int k, 
 // ---------------------------------------------------------------------------------------------
 // K4: candidates -> exact fp32 rescore -> certificate -> final top-k
 // ---------------------------------------------------------------------------------------------
-// One CTA (256 threads) per query.  Candidates come from a bf16 prefilter whose invariant is:
+// One CTA per query (256 threads; 1024 when the batch is too small to fill the chip with 256-thread
+// CTAs, so that a lone query's ~256 row gathers are spread over 32 warps).  Candidates come from a bf16 prefilter whose invariant is:
 // every row NOT in the list has prefilter score <= thr[q].  Let eps bound |prefilter - exact|.
 // After rescoring the best m candidates (by prefilter score) exactly, the exact top-k of those m
 // is the exact top-k of the whole corpus if  exact_k > max(next prefilter score, thr) + eps.
@@ -254,7 +255,7 @@ __device__ __forceinline__ float exact_score_warp(const float* __restrict__ xr, 
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(256) k4_rescore_kernel(RescoreArgs a) {
+__global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: keys[cap] u64 | ekeys[cap] u64 | q[d] f32
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
@@ -369,14 +370,15 @@ int launch_rescore(const RescoreArgs& a, cudaStream_t st) {
     if (a.nq <= 0) return TRX_OK;
     size_t smem = (size_t)a.cap * 16 + (size_t)a.d * 4;
     if (smem > 200 * 1024) { set_error("k4: cap=%d d=%d exceed shared memory", a.cap, a.d); return TRX_EINVAL; }
+    const int threads = a.nq <= 296 ? 1024 : 256;
     if (a.metric == TRX_METRIC_L2) {
         auto kern = k4_rescore_kernel<TRX_METRIC_L2>;
         TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)a.nq, 256, smem, st>>>(a);
+        kern<<<(unsigned)a.nq, threads, smem, st>>>(a);
     } else {
         auto kern = k4_rescore_kernel<TRX_METRIC_INNER_PRODUCT>;
         TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)a.nq, 256, smem, st>>>(a);
+        kern<<<(unsigned)a.nq, threads, smem, st>>>(a);
     }
     count_launch();
     TRX_CUDA(cudaGetLastError());
@@ -474,7 +476,8 @@ __global__ void __launch_bounds__(256) slot_thr_kernel(const float* __restrict__
 
 int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st) {
     if (nq <= 0) return TRX_OK;
-    if (S > 8 || r > 32 * S) { set_error("slot_thr: S=%d r=%d unsupported", S, r); return TRX_EINVAL; }
+    if (r > 32 * S) { set_error("slot_thr: S=%d r=%d unsupported", S, r); return TRX_EINVAL; }
+    if (S > 8) return launch_row_kth(slots, (int64_t)S * 32, (int64_t)S * 32, nq, r, thr, st);  // small batches: many slices
     slot_thr_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(slots, nq, S, r, thr);
     count_launch();
     TRX_CUDA(cudaGetLastError());

@@ -119,6 +119,7 @@ struct trx_index {
     int32_t* fb_list2 = nullptr; float* thr2 = nullptr;   // second-chance (threshold-guided) lists
     float* qfb = nullptr; int32_t* exfb = nullptr;
     float* xscores = nullptr; size_t xscores_elems = 0;  // exact-path score rows
+    uint32_t* h_nfb = nullptr;       // pinned: fallback count read back once per batch
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     trx_stats_t st{};
@@ -174,7 +175,8 @@ static int ensure_ws(trx_index* ix, int B, int k, int cap) {
         dfree(ix->fb_thr); dfree(ix->eps_acc); dfree(ix->neg_inf); dfree(ix->fb_list2); dfree(ix->thr2);
         dfree(ix->Dd); dfree(ix->Id); ix->ws_k = 0;
         TRX_TRY(dmalloc(&ix->q32, (size_t)nb * ix->d));
-        TRX_TRY(dmalloc(&ix->q16, (size_t)nb * ix->Kp));
+        TRX_TRY(dmalloc(&ix->q16, (size_t)(nb + 8) * ix->Kp));   // K2 moves round8(nq) query rows
+        TRX_CUDA(cudaMemset(ix->q16, 0, (size_t)(nb + 8) * ix->Kp * 2));
         TRX_TRY(dmalloc(&ix->qnorm2, (size_t)nb));
         TRX_TRY(dmalloc(&ix->eps, (size_t)nb));
         TRX_TRY(dmalloc(&ix->thr, (size_t)nb));
@@ -278,26 +280,25 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
         path = TRX_PATH_EXACT;  // prefilter needs a corpus larger than the candidate list
     }
     ix->st.last_path = path;
+    bool results_sent = false;
     if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[0], st));
 
     if (path == TRX_PATH_EXACT) {
         TRX_TRY(run_exact(ix, qdev, exdev, nullptr, B, k, st));
     } else {
         TRX_TRY(ensure_sample(ix, st));
-        TRX_TRY(launch_query_prep(qdev, B, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, st));
-        TRX_TRY(launch_eps(ix->qnorm2, ix->norm2_max, B, ix->d, ix->metric, ix->eps, ix->eps_acc, st));
-        TRX_CUDA(cudaMemsetAsync(ix->cand_cnt, 0, (size_t)B * 4, st));
-        TRX_CUDA(cudaMemsetAsync(ix->fb_count, 0, 4, st));
+        TRX_TRY(launch_query_prep(qdev, B, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, ix->norm2_max, ix->eps,
+                                  ix->eps_acc, ix->cand_cnt, ix->fb_count, st));
         const int T = std::max(ix->target, 4 * k);
         int r = std::max(1, (T + ix->sample_rate / 2) / ix->sample_rate);
 
         if (path == TRX_PATH_UMMA) {
-            const int S = umma_num_slices(ix->ns);
-            size_t need = (size_t)B * S * 32;
-            if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
             UmmaArgs u{};
             u.q16 = ix->q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
             u.pair = ix->umma_pair && B > 128;
+            const int S = umma_num_slices(ix->ns, B, ix->sm_count, u.pair);
+            size_t need = (size_t)B * S * 32;
+            if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
             u.mode = 2; u.out = ix->slots;
             TRX_TRY(launch_umma(u, ix->sm_count, st));
             TRX_TRY(launch_slot_thr(ix->slots, B, S, std::min(r, 32 * S), ix->thr, st));
@@ -349,9 +350,15 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
         ra.fb_thr = ix->fb_thr; ra.eps_acc = ix->eps_acc; ra.qmap = nullptr; ra.counters = ix->counters;
         TRX_TRY(launch_rescore(ra, st));
 
-        uint32_t nfb = 0;
-        TRX_CUDA(cudaMemcpyAsync(&nfb, ix->fb_count, 4, cudaMemcpyDeviceToHost, st));
+        // Common case (every query certified): the results leave with the same synchronisation that
+        // reads the fallback count.  Otherwise the fallback fills the missing rows and they are sent again.
+        TRX_CUDA(cudaMemcpyAsync(ix->h_nfb, ix->fb_count, 4, cudaMemcpyDeviceToHost, st));
+        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[3], st));
+        TRX_CUDA(cudaMemcpyAsync(D, ix->Dd, (size_t)B * k * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        TRX_CUDA(cudaMemcpyAsync(I, ix->Id, (size_t)B * k * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
         TRX_CUDA(cudaStreamSynchronize(st));
+        const uint32_t nfb = *ix->h_nfb;
+        results_sent = nfb == 0;
         if (nfb > 0) {
             // Queries without a certificate.  Second chance, still exact: K4 left the k-th best exact
             // score it saw; every true top-k row scores at least that, so one fp32 streaming pass
@@ -421,11 +428,12 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
             }
         }
     }
-    if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[3], st));
-
-    TRX_CUDA(cudaMemcpyAsync(D, ix->Dd, (size_t)B * k * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    TRX_CUDA(cudaMemcpyAsync(I, ix->Id, (size_t)B * k * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    if (!out_dev || !xq_dev || ix->timing) TRX_CUDA(cudaStreamSynchronize(st));
+    if (!results_sent) {
+        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[3], st));
+        TRX_CUDA(cudaMemcpyAsync(D, ix->Dd, (size_t)B * k * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        TRX_CUDA(cudaMemcpyAsync(I, ix->Id, (size_t)B * k * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (!out_dev || !xq_dev || ix->timing) TRX_CUDA(cudaStreamSynchronize(st));
+    }
     if (ix->timing) {
         float ms = 0.f;
         TRX_CUDA(cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]));
@@ -477,6 +485,7 @@ int trx_create(int d, int metric, int device, trx_index** out) {
         if ((rc = dmalloc(&ix->fb_count, 1)) != TRX_OK) break;
         if ((rc = dmalloc(&ix->counters, 4)) != TRX_OK) break;
         if (cudaMemset(ix->norm2_max, 0, 4) != cudaSuccess || cudaMemset(ix->counters, 0, 32) != cudaSuccess ||
+            cudaHostAlloc((void**)&ix->h_nfb, 64, cudaHostAllocDefault) != cudaSuccess ||
             cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
             set_error("device init failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = TRX_ECUDA; break;
@@ -496,6 +505,7 @@ void trx_destroy(trx_index* ix) {
     cudaDeviceSynchronize();
     free_ws(ix); free_store(ix);
     dfree(ix->norm2_max); dfree(ix->fb_count); dfree(ix->counters);
+    if (ix->h_nfb) { cudaFreeHost(ix->h_nfb); ix->h_nfb = nullptr; }
     for (int i = 0; i < 4; i++) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
@@ -650,7 +660,8 @@ int trx_debug_scores_umma(trx_index* ix, const float* xq, int64_t nq, int64_t ro
     DeviceGuard g(ix->device);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
     TRX_TRY(ensure_ws(ix, (int)nq, 1, candidate_cap(ix, 1)));
-    TRX_TRY(launch_query_prep(xq, nq, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, st));
+    TRX_TRY(launch_query_prep(xq, nq, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, st));
     UmmaArgs u{};
     u.q16 = ix->q16; u.nq = nq; u.x16 = ix->x16 + row0 * ix->Kp; u.n = n; u.Kp = ix->Kp;
     u.mode = 0; u.out = out; u.out_ld = n;

@@ -33,6 +33,14 @@ except Exception:  # pragma: no cover
     torch = None
 
 
+_CUDA_STREAM_LEGACY = 0x1   # cudaStreamLegacy: the C ABI reads a NULL stream as "use the index's own stream"
+
+
+def _stream_handle(device):
+    """torch's current stream on `device` as a non-NULL handle (the default stream has handle 0)."""
+    return torch.cuda.current_stream(device).cuda_stream or _CUDA_STREAM_LEGACY
+
+
 def _is_torch(x):
     return torch is not None and isinstance(x, torch.Tensor)
 
@@ -85,7 +93,9 @@ class IndexFlat:
 
     # -- FAISS methods ----------------------------------------------------------------------
     def add(self, x):
-        ptr, n, keep, _ = _as_f32_matrix(x, self.d)
+        ptr, n, keep, on_dev = _as_f32_matrix(x, self.d)
+        if on_dev:   # trx_add copies on the index's own stream: the producer of `x` must have finished
+            torch.cuda.current_stream(keep.device).synchronize()
         _lib.check(self._L.trx_add(self._h, ptr, n), "add")
         del keep
 
@@ -102,7 +112,7 @@ class IndexFlat:
             assert Dt.shape == (nq, k) and It.shape == (nq, k) and Dt.is_contiguous() and It.is_contiguous()
             assert Dt.dtype == torch.float32 and It.dtype == torch.int64 and Dt.is_cuda and It.is_cuda
             dptr, iptr = Dt.data_ptr(), It.data_ptr()
-            stream = torch.cuda.current_stream(keep.device).cuda_stream
+            stream = _stream_handle(keep.device)
             out = (Dt, It)
         else:
             Dn = D if D is not None else np.empty((nq, k), dtype=np.float32)
@@ -129,6 +139,8 @@ class IndexFlat:
             _lib.check(self._L.trx_set_groups(self._h, None, 0), "set_groups")
             return
         ptr, keep = _as_i32_vector(groups, self.ntotal, "groups")
+        if _is_torch(keep) and keep.is_cuda:
+            torch.cuda.current_stream(keep.device).synchronize()
         _lib.check(self._L.trx_set_groups(self._h, ptr, self.ntotal), "set_groups")
         del keep
 
@@ -154,7 +166,7 @@ class IndexFlat:
         assert on_dev, "debug_scores_umma takes a CUDA tensor"
         out = torch.empty((nq, n), dtype=torch.float32, device=keep.device)
         _lib.check(self._L.trx_debug_scores_umma(self._h, ptr, nq, int(row0), int(n), out.data_ptr(),
-                                                 torch.cuda.current_stream(keep.device).cuda_stream), "debug_scores")
+                                                 _stream_handle(keep.device)), "debug_scores")
         return out
 
     def close(self):
@@ -189,5 +201,5 @@ def merge_topk(Dg, Ig, metric):
     I = torch.empty((nq, k), dtype=torch.int64, device=Dg.device)
     L = _lib.lib()
     _lib.check(L.trx_merge_topk(int(metric), Dg.data_ptr(), Ig.data_ptr(), G, nq, k, D.data_ptr(), I.data_ptr(),
-                                torch.cuda.current_stream(Dg.device).cuda_stream), "merge_topk")
+                                _stream_handle(Dg.device)), "merge_topk")
     return D, I

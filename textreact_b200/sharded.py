@@ -30,6 +30,7 @@ class ShardedIndexFlat:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.d, self.metric_type = int(d), int(metric)
+        self._on_cuda = local_factory is None          # the product path; test doubles stay on the host
         self.local = (local_factory or (lambda d_, m_: IndexFlat(d_, m_, device=device)))(d, metric)
         self._merge = merge_fn or merge_topk
         self._ntotal_global = 0
@@ -57,10 +58,18 @@ class ShardedIndexFlat:
         self.local.set_groups(groups[lo:hi])
 
     def search(self, xq, k, *, exclude=None):
-        """xq replicated on every rank.  Returns (D, I) on every rank."""
+        """xq replicated on every rank.  Returns (D, I) on every rank (numpy in -> numpy out)."""
+        as_numpy = not (isinstance(xq, torch.Tensor) and xq.is_cuda)
+        if as_numpy and self._on_cuda:
+            # the exchange runs over NCCL: keep the per-shard lists on the device, one H2D / D2H per call
+            dev = torch.device("cuda", self.local.device)
+            if isinstance(xq, torch.Tensor):
+                xq = xq.detach().cpu().numpy()
+            xq = torch.from_numpy(np.ascontiguousarray(xq, dtype=np.float32)).to(dev)
+            if exclude is not None and not (isinstance(exclude, torch.Tensor) and exclude.is_cuda):
+                exclude = torch.as_tensor(np.ascontiguousarray(exclude, dtype=np.int32)).to(dev)
         D, I = self.local.search(xq, k, exclude=exclude)
-        as_numpy = not isinstance(D, torch.Tensor)
-        if as_numpy:
+        if not isinstance(D, torch.Tensor):
             D, I = torch.from_numpy(D), torch.from_numpy(I)
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
         Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
