@@ -208,3 +208,35 @@ def test_merge_topk_equals_unsharded():
         Ds.append(Dg); Is.append(Ig); idx.close()
     D, I = trx.merge_topk(torch.stack(Ds), torch.stack(Is), IP)
     oracle.check_parity(D.cpu().numpy(), I.cpu().numpy(), xb, xq, k, IP)
+
+
+def test_candidate_overflow_falls_back_to_exact_scan():
+    """6000 identical rows that are the best match of some queries: more rows above any threshold than a
+    candidate list holds (4096).  Those queries must come back exact (generic fp32 scan + radix select),
+    ties in ascending id order; the others stay on the prefilter path."""
+    trx = _engine()
+    n, d, nq, k = 60000, 256, 130, 20
+    xb, xq = util.gaussian(n, d, 101), util.gaussian(nq, d, 102)
+    hot = xq[:8].sum(0)
+    hot *= 3.0 / np.linalg.norm(hot) * np.sqrt(d)
+    xb[1000:7000] = hot
+    D, I, st = _run(xb, xq, k, IP, trx.PATH_UMMA)
+    oracle.check_parity(D, I, xb, xq, k, IP)
+    assert st["queries_overflow"] >= 8 and st["queries_exact"] >= 8, st
+    assert (I[:8] == np.arange(1000, 1000 + k)).all()
+
+
+@pytest.mark.parametrize("path_name", ["stream", "umma"])
+def test_ascending_score_corpus(path_name):
+    """Dist A of SURVEY 8d: row norms grow with the row id, so the best rows all sit at the end of the
+    scan -- the worst case for a running-threshold design; the sampled threshold must not care."""
+    trx = _engine()
+    path = {"stream": trx.PATH_STREAM, "umma": trx.PATH_UMMA}[path_name]
+    n, d, k = 80000, 768, 100
+    nq = 5 if path_name == "stream" else 200
+    xb = util.gaussian(n, d, 111) * (0.25 + 1.5 * np.arange(n, dtype=np.float32)[:, None] / n)
+    xq = util.gaussian(nq, d, 112)
+    D, I, st = _run(xb, xq, k, IP, path)
+    oracle.check_parity(D, I, xb, xq, k, IP)
+    assert st["last_path"] == path
+    assert np.median(I) > 0.6 * n

@@ -59,16 +59,31 @@ __device__ void block_radix_select(const float* __restrict__ s, int64_t n, uint3
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t cum = 0;
-            int b = 255;
-            for (; b > 0; b--) {
-                uint32_t c = hist[b];
-                if (cum + c >= remaining) break;
-                cum += c;
+        if (threadIdx.x < 32) {
+            // warp-parallel scan from the top bin down: lane l owns bins [8l, 8l+8)
+            const int ln = threadIdx.x;
+            uint32_t c[8], local = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { c[j] = hist[ln * 8 + j]; local += c[j]; }
+            uint32_t incl = local;   // inclusive suffix sum over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+                if (ln + o < 32) incl += t;
             }
-            bc[0] = (uint32_t)b;
-            bc[1] = cum;
+            const uint32_t above = incl - local;   // elements in the bins of higher lanes
+            const bool crossing = above < remaining && remaining <= above + local;
+            const bool underflow = ln == 0 && remaining > above + local;   // fewer than `remaining` elements: bin 0
+            if (crossing || underflow) {
+                uint32_t cum = above;
+                int b = 7;
+                for (; b > 0; b--) {
+                    if (cum + c[b] >= remaining) break;
+                    cum += c[b];
+                }
+                bc[0] = (uint32_t)(ln * 8 + b);
+                bc[1] = cum;
+            }
         }
         __syncthreads();
         prefix |= bc[0] << shift;
@@ -100,12 +115,19 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* scratch 
 // ---------------------------------------------------------------------------------------------
 // row_kth: threshold = r-th largest of a materialised score row (K3 sample pass)
 // ---------------------------------------------------------------------------------------------
+constexpr int kRowKthSmem = 8192;
 __global__ void __launch_bounds__(512) row_kth_kernel(const float* __restrict__ s, int64_t ld, int64_t n, int r,
                                                       float* __restrict__ thr) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t bc[4];
     __shared__ uint32_t scratch[33];
+    __shared__ float srow[kRowKthSmem];
     const float* row = s + (int64_t)blockIdx.x * ld;
+    if (n <= kRowKthSmem) {   // short rows (slot maxima of a small batch): one coalesced read, passes from smem
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) srow[i] = row[i];
+        __syncthreads();
+        row = srow;
+    }
     uint32_t fin = 0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) fin += row[i] > -INFINITY ? 1u : 0u;
     fin = block_sum_u32(fin, scratch);

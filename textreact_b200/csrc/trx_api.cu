@@ -3,7 +3,7 @@
 // Pipeline of one trx_search batch (B <= max_batch queries):
 //
 //   K1 query_prep   fp32 queries -> bf16 (+|q|^2), certificate slack eps
-//   pass 0          scorer over the 1/32 row sample -> per-query threshold thr (target: ~T rows
+//   pass 0          K2 (tcgen05) over the 1/32 row sample -> per-query threshold thr (target: ~T rows
 //                   of the corpus score above it)
 //   main pass       scorer over the whole bf16 corpus, candidates with score > thr appended
 //                   (K2 tcgen05 for batches, K3 CUDA-core streaming for tiny batches)
@@ -292,21 +292,24 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
         const int T = std::max(ix->target, 4 * k);
         int r = std::max(1, (T + ix->sample_rate / 2) / ix->sample_rate);
 
+        // pass 0 (both prefilter paths): tcgen05 scores of the batch against the 1/32 row sample, slot maxima,
+        // r-th largest -> per-query threshold that ~T corpus rows are expected to beat
+        UmmaArgs u{};
+        u.q16 = ix->q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
+        u.pair = ix->umma_pair && B > 128;
+        const int S = umma_num_slices(ix->ns, B, ix->sm_count, u.pair);
+        size_t need = (size_t)B * S * 32;
+        if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
+        u.mode = 2; u.out = ix->slots;
+        TRX_TRY(launch_umma(u, ix->sm_count, st));
+        TRX_TRY(launch_slot_thr(ix->slots, B, S, std::min(r, 32 * S), ix->thr, st));
+        if (ix->thr_bias != 0.f) {
+            add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(ix->thr, (int)B, ix->thr_bias);
+            count_launch();
+        }
+        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[1], st));
+
         if (path == TRX_PATH_UMMA) {
-            UmmaArgs u{};
-            u.q16 = ix->q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
-            u.pair = ix->umma_pair && B > 128;
-            const int S = umma_num_slices(ix->ns, B, ix->sm_count, u.pair);
-            size_t need = (size_t)B * S * 32;
-            if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
-            u.mode = 2; u.out = ix->slots;
-            TRX_TRY(launch_umma(u, ix->sm_count, st));
-            TRX_TRY(launch_slot_thr(ix->slots, B, S, std::min(r, 32 * S), ix->thr, st));
-            if (ix->thr_bias != 0.f) {
-                add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(ix->thr, (int)B, ix->thr_bias);
-                count_launch();
-            }
-            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[1], st));
             u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
             u.thr = ix->thr; u.cand = ix->cand; u.cand_cnt = ix->cand_cnt; u.cap = cap;
             {   // private hit logs: 3x the expected hits per epilogue thread, at least 256 entries
@@ -324,22 +327,16 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
                 u.log = ix->hitlog; u.log_cnt = ix->hitlog_cnt; u.log_cap = log_cap;
             }
             TRX_TRY(launch_umma(u, ix->sm_count, st));
-            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[2], st));
         } else {
-            size_t need = (size_t)B * ix->ns;
-            if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
+            // main pass on the CUDA cores: one sweep over the bf16 corpus per 4 queries, hits appended directly
             StreamArgs a{};
-            a.x = ix->xs16; a.pitch = ix->Kp; a.n = ix->ns; a.d = ix->Kp;
+            a.x = ix->x16; a.pitch = ix->Kp; a.n = N; a.d = ix->Kp;
             a.q16 = ix->q16; a.q_pitch = ix->Kp; a.nq = B;
-            a.out = ix->slots; a.out_ld = ix->ns; a.metric = TRX_METRIC_INNER_PRODUCT; a.bf16 = true; a.append = false;
-            TRX_TRY(launch_stream(a, ix->sm_count, st));
-            TRX_TRY(launch_row_kth(ix->slots, ix->ns, ix->ns, B, (int)std::min<int64_t>(r, ix->ns), ix->thr, st));
-            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[1], st));
-            a.x = ix->x16; a.n = N; a.out = nullptr; a.append = true;
+            a.metric = TRX_METRIC_INNER_PRODUCT; a.bf16 = true; a.append = true;
             a.thr = ix->thr; a.cand = ix->cand; a.cand_cnt = ix->cand_cnt; a.cap = cap;
             TRX_TRY(launch_stream(a, ix->sm_count, st));
-            if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[2], st));
         }
+        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[2], st));
 
         RescoreArgs ra{};
         ra.cand = ix->cand; ra.cand_cnt = ix->cand_cnt; ra.cap = cap; ra.thr = ix->thr; ra.eps = ix->eps;
