@@ -337,8 +337,14 @@ def main():
     kern_ms = sum(pre_ms) / len(pre_ms)
     flops = 2.0 * batch * (hi - lo) * D_MODEL
     achieved_tf = flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    traffic = None   # dram bytes per launch of the dominant kernel: from the committed ncu --set full capture (C2 only)
+    tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if world == 1 and not args.rows and not args.batch and os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("traffic_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["tf_sust"], "traffic": None,
+                "frac": achieved_tf / pk["tf_sust"], "traffic": traffic,
+                "traffic_source": "profiles/k2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None,
                 "kernel": "k2_umma_kernel<THRESH> (tcgen05 bf16 scoring + fused threshold select)",
                 "kernel_ms": kern_ms, "batch_ms_on_device": sum(tot_ms) / len(tot_ms),
                 "peak_kind": f"{pk['src']} cuBLAS bf16 sustained; burst {pk['tf_burst']}",

@@ -103,7 +103,8 @@ int trx_metric(const trx_index* idx);
 int trx_set_id_offset(trx_index* idx, int64_t offset);
 
 /* Tunables: "path" (TRX_PATH_*), "max_batch", "target_candidates", "sample_rate",
- * "stream_max_batch" (crossover below which AUTO uses the streaming kernel), "timing". */
+ * "stream_max_batch" (crossover at or below which AUTO uses the streaming kernel),
+ * "umma_pair" / "pair_min_batch" (CTA-pair tiling from this batch size on), "timing". */
 int trx_set_option(trx_index* idx, const char* key, double value);
 int trx_get_option(const trx_index* idx, const char* key, double* value);
 

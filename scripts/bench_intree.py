@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""scripts/bench_intree.py -- the workload the in-tree script actually runs, on one B200.
+
+retrieve/retrieve_faiss.py:62-74 builds `faiss.IndexFlatL2(d)` over RDKit fingerprints and searches k=20:
+  * Morgan bits      d=1024, 0/1, int8          (:36-44)   --field product_smiles (retro.sh, retro_year.sh)
+  * difference FPs   d=2048, small signed counts, int64 (:18-27)   --field canonical_rxn (condition_year.sh)
+and the first of its three searches is train->train (nq == N, :114-115).  RDKit is not available here, so
+the fingerprints are synthetic with the same dtype / sparsity; distances are integers, ties are massive,
+and the bf16 prefilter is exact -- what matters is how often the sampled threshold / certificate sends a
+query to the exact fp32 scan.  Reports q/s for a slice of the train->train search, the engine's path
+statistics, bit-exact parity of a sample against the CPU oracle, and the oracle's own q/s on the host cores.
+
+  python scripts/bench_intree.py [--rows 1000000] [--queries 65536] [--out gpurun_out/intree.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import textreact_b200 as trx  # noqa: E402
+from oracle import cpu_flat as oracle  # noqa: E402  (checker + cpu baseline only)
+
+
+def morgan_like(n, d, seed):
+    rng = np.random.default_rng(seed)
+    # per-row density varies (molecule size): 2%..8% bits set
+    dens = rng.uniform(0.02, 0.08, size=(n, 1)).astype(np.float32)
+    return (rng.random((n, d), dtype=np.float32) < dens).astype(np.int8)
+
+
+def difference_like(n, d, seed):
+    rng = np.random.default_rng(seed)
+    mask = rng.random((n, d), dtype=np.float32) < 0.02
+    return (rng.integers(-3, 4, size=(n, d), dtype=np.int8) * mask).astype(np.int64)
+
+
+def run(name, xb, nq, k, batch, check):
+    n, d = xb.shape
+    idx = trx.IndexFlatL2(d)
+    t0 = time.perf_counter()
+    idx.add(xb)
+    t_add = time.perf_counter() - t0
+    xq = xb[:nq]
+    idx.search(xq[:batch], k)                       # warm-up (workspaces, sample)
+    torch.cuda.synchronize()
+    s0 = idx.stats()
+    t0 = time.perf_counter()
+    D, I = idx.search(xq, k)                        # the script's call: host arrays in, host arrays out
+    dt = time.perf_counter() - t0
+    s1 = idx.stats()
+    st = {key: s1[key] - s0[key] for key in ("queries", "queries_exact", "queries_uncert", "queries_overflow",
+                                             "rescored", "candidates")}
+    assert (I[:, 0] >= 0).all() and (D[:, 0] == 0).all()          # self match at distance 0 first
+    Do, Io = oracle.search_seq(xb, xq[:check], k, 1)
+    exact = bool((Do == D[:check]).all() and (Io == I[:check]).all())
+    t0 = time.perf_counter()
+    oracle.search_blas(xb, xq[:1024], k, 1)
+    cpu_qps = 1024 / (time.perf_counter() - t0)
+    rec = {"workload": name, "rows": n, "d": d, "dtype": str(xb.dtype), "k": k, "queries": nq, "metric": "L2",
+           "seconds": dt, "qps": nq / dt, "add_seconds": t_add, "engine": st,
+           "fallback_fraction": st["queries_exact"] / max(st["queries"], 1),
+           "bit_exact_vs_oracle_first": check, "bit_exact": exact,
+           "cpu_oracle_qps": cpu_qps, "cpu_threads": os.cpu_count()}
+    idx.close()
+    print(json.dumps(rec), flush=True)
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--queries", type=int, default=65536)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "intree.json"))
+    args = ap.parse_args()
+    out = []
+    out.append(run("morgan-like bits (retro.sh / retro_year.sh)", morgan_like(args.rows, 1024, 1), args.queries, 20, 8192, 64))
+    out.append(run("difference-FP-like counts (condition_year.sh)", difference_like(args.rows // 2, 2048, 2),
+                   args.queries, 20, 8192, 64))
+    with open(args.out, "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

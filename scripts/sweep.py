@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--reps", type=int, default=200)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--skip-c3", action="store_true")
-    ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256")
+    ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,192,256,384,512,1024")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -63,10 +63,13 @@ def main():
         qs = [torch.randn((B, D_MODEL), generator=qgen, device=dev, dtype=torch.float32).cpu().numpy() for _ in range(8)]
         D = np.empty((B, K), np.float32)
         I = np.empty((B, K), np.int64)
-        for name, path in (("stream", trx.PATH_STREAM), ("umma", trx.PATH_UMMA)):
+        for name, path in (("stream", trx.PATH_STREAM), ("umma", trx.PATH_UMMA), ("umma_single_cta", trx.PATH_UMMA)):
             if name == "stream" and B > 8:
                 continue
+            if name == "umma_single_cta" and B <= 128:
+                continue                      # batches up to 128 queries are single-CTA tiles anyway
             idx.set_option("path", path)
+            idx.set_option("umma_pair", 0 if name == "umma_single_cta" else 1)
             idx.set_option("timing", 1)
             for i in range(5):
                 idx.search(qs[i % 8], K, D=D, I=I)
@@ -96,6 +99,7 @@ def main():
             out["c5"].append(rec)
             print(json.dumps(rec), flush=True)
     idx.set_option("path", trx.PATH_AUTO)
+    idx.set_option("umma_pair", 1)
 
     # ---- C3 ---------------------------------------------------------------------------------------
     if not args.skip_c3:

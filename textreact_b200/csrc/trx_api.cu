@@ -102,9 +102,11 @@ struct trx_index {
     int max_batch = 8192;
     int target = 768;       // expected candidates per query
     int sample_rate = 32;
-    int stream_max_batch = 0;  // AUTO: batches <= this use the K3 streaming prefilter
+    int stream_max_batch = 1;  // AUTO: batches <= this use the K3 streaming prefilter (measured crossover,
+                               // profiles/r1i_summary.md: K3 wins at batch 1, K2 from batch 2 on)
     int timing = 0;
-    int umma_pair = 1;      // use the CTA-pair (cta_group::2) tiling when the batch has > 128 queries
+    int umma_pair = 1;      // allow the CTA-pair (cta_group::2) tiling
+    int pair_min_batch = 129;  // ... for batches of at least this many queries (measured crossover)
     float thr_bias = 0.f;   // experiments only: added to every estimated threshold
     // workspaces (sized for max_batch)
     int ws_batch = 0, ws_cap = 0;
@@ -296,7 +298,7 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
         // r-th largest -> per-query threshold that ~T corpus rows are expected to beat
         UmmaArgs u{};
         u.q16 = ix->q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
-        u.pair = ix->umma_pair && B > 128;
+        u.pair = ix->umma_pair && B >= ix->pair_min_batch;
         const int S = umma_num_slices(ix->ns, B, ix->sm_count, u.pair);
         size_t need = (size_t)B * S * 32;
         if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
@@ -611,6 +613,9 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->thr_bias = (float)v;
     } else if (!strcmp(key, "umma_pair")) {
         ix->umma_pair = v != 0;
+    } else if (!strcmp(key, "pair_min_batch")) {
+        if (v < 1) { set_error("pair_min_batch out of range"); return TRX_EINVAL; }
+        ix->pair_min_batch = (int)v;
     } else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
@@ -624,6 +629,7 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "stream_max_batch")) *v = ix->stream_max_batch;
     else if (!strcmp(key, "timing")) *v = ix->timing;
     else if (!strcmp(key, "umma_pair")) *v = ix->umma_pair;
+    else if (!strcmp(key, "pair_min_batch")) *v = ix->pair_min_batch;
     else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
@@ -662,7 +668,7 @@ int trx_debug_scores_umma(trx_index* ix, const float* xq, int64_t nq, int64_t ro
     UmmaArgs u{};
     u.q16 = ix->q16; u.nq = nq; u.x16 = ix->x16 + row0 * ix->Kp; u.n = n; u.Kp = ix->Kp;
     u.mode = 0; u.out = out; u.out_ld = n;
-    u.pair = ix->umma_pair && nq > 128;
+    u.pair = ix->umma_pair && nq >= ix->pair_min_batch;
     TRX_TRY(launch_umma(u, ix->sm_count, st));
     TRX_CUDA(cudaStreamSynchronize(st));
     return TRX_OK;
