@@ -21,9 +21,10 @@
  *     status (TRX_OK == 0) and leaves a message retrievable with trx_last_error()
  *     (thread-local).
  *   - `x`, `xq`, `excl`, `g`, `D`, `I` may each be HOST or DEVICE pointers (detected with
- *     cudaPointerGetAttributes).  Host-pointer calls are synchronous on return;
- *     device-pointer calls are ordered on `stream` and additionally synchronised before
- *     return only when the exact-fallback path has to be consulted.
+ *     cudaPointerGetAttributes).  Every call is complete on return: trx_search waits for
+ *     its last batch (it has to read the count of queries that need the exact fallback).
+ *     Work is ordered on `stream` (NULL: the index's own stream); inside one call the
+ *     batches are software-pipelined (upload and launch of batch i+1 overlap batch i).
  *   - the caller owns every buffer it passes; the index owns its device copies
  *     (fp32 corpus, bf16 corpus, norms, groups, workspaces) until reset/destroy.
  *   - results: best first (IP: larger score; L2: smaller squared distance), ties by
@@ -104,7 +105,8 @@ int trx_set_id_offset(trx_index* idx, int64_t offset);
 
 /* Tunables: "path" (TRX_PATH_*), "max_batch", "target_candidates", "sample_rate",
  * "stream_max_batch" (crossover at or below which AUTO uses the streaming kernel),
- * "umma_pair" / "pair_min_batch" (CTA-pair tiling from this batch size on), "timing". */
+ * "umma_pair" / "pair_min_batch" (CTA-pair tiling from this batch size on),
+ * "pipeline" (0: serial batches), "timing". */
 int trx_set_option(trx_index* idx, const char* key, double value);
 int trx_get_option(const trx_index* idx, const char* key, double* value);
 

@@ -7,6 +7,7 @@
       for the CUDA-core streaming prefilter (K3) and the tcgen05 prefilter (K2): the measured
       crossover between the two is what `stream_max_batch` defaults to.
   C3  gold-removed mode: C2 shape with a per-query exclusion group (group = row // 5).
+  C2 full job (--full-job 700000): the whole USPTO-scale query set through one `index.search` call.
 
   python scripts/sweep.py [--rows N] [--out gpurun_out/sweep.json] [--reps 200]
 """
@@ -38,6 +39,7 @@ def main():
     ap.add_argument("--reps", type=int, default=200)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--skip-c3", action="store_true")
+    ap.add_argument("--full-job", type=int, default=0, help="also run this many queries (C2: 700000) as one call")
     ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,192,256,384,512,1024")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -129,6 +131,38 @@ def main():
         res["stats"] = {k: v for k, v in idx.stats().items() if k.startswith("queries")}
         out["c3"] = res
         print(json.dumps({"c3": res}), flush=True)
+
+    # ---- C2 as one job: 700K queries through ONE index.search call, pageable host arrays in and out ----
+    if args.full_job:
+        nq = args.full_job
+        idx.set_groups(None)
+        idx.set_option("max_batch", 4096)
+        hq = np.empty((nq, D_MODEL), np.float32)
+        for c0 in range(0, nq, 65536):
+            c1 = min(nq, c0 + 65536)
+            hq[c0:c1] = torch.randn((c1 - c0, D_MODEL), generator=qgen, device=dev, dtype=torch.float32).cpu().numpy()
+        idx.search(hq[:8192], K)
+        idx.set_option("pipeline", 0)
+        t0 = time.perf_counter()
+        idx.search(hq[:nq // 4], K)
+        dt_serial = (time.perf_counter() - t0) * 4
+        idx.set_option("pipeline", 1)
+        s0 = idx.stats()
+        t0 = time.perf_counter()
+        Dj, Ij = idx.search(hq, K)
+        dt = time.perf_counter() - t0
+        s1 = idx.stats()
+        res = {"queries": nq, "batch": 4096, "seconds": dt, "qps": nq / dt, "host_buffers": "pageable numpy",
+               "qps_serial_batches": nq / dt_serial,
+               "h2d_bytes": hq.nbytes, "d2h_bytes": Dj.nbytes + Ij.nbytes,
+               "queries_exact": s1["queries_exact"] - s0["queries_exact"],
+               "queries_uncert": s1["queries_uncert"] - s0["queries_uncert"]}
+        # self-consistency of the big job: a late slice re-run alone returns the same rows
+        D2, I2 = idx.search(hq[nq - 1000:], K)
+        res["tail_slice_identical"] = bool((I2 == Ij[nq - 1000:]).all() and (D2 == Dj[nq - 1000:]).all())
+        out["c2_full_job"] = res
+        print(json.dumps({"c2_full_job": res}), flush=True)
+        idx.set_option("max_batch", 8192)
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:

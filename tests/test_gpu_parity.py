@@ -247,3 +247,72 @@ def test_ascending_score_corpus(path_name):
     oracle.check_parity(D, I, xb, xq, k, IP)
     assert st["last_path"] == path
     assert np.median(I) > 0.6 * n
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("d", [100, 333, 1000])
+def test_dimensions_that_are_not_tile_multiples(metric, d):
+    """d not a multiple of 64 (bf16 rows are zero padded to the TMA tile) nor of 4 (fp32 rows are not
+    16-byte aligned: scalar-load variants of the exact scorer and of the rescore)."""
+    trx = _engine()
+    n, nq, k = 30000, 150, 10
+    xb, xq = util.gaussian(n, d, 121), util.gaussian(nq, d, 122)
+    for path in (trx.PATH_UMMA, trx.PATH_STREAM, trx.PATH_EXACT):
+        q = xq if path == trx.PATH_UMMA else xq[:5]
+        D, I, st = _run(xb, q, k, metric, path)
+        oracle.check_parity(D, I, xb, q, k, metric)
+        assert st["last_path"] == path
+
+
+@pytest.mark.parametrize("k", [1, 100, 256, 300, 1000])
+def test_k_range(k):
+    """k up to 256 stays on the prefilter path (candidate lists grow with k); beyond that the exact scan."""
+    trx = _engine()
+    n, d, nq = 40000, 128, 140
+    xb, xq = util.gaussian(n, d, 131), util.gaussian(nq, d, 132)
+    D, I, st = _run(xb, xq, k, IP, trx.PATH_AUTO)
+    oracle.check_parity(D, I, xb, xq, k, IP)
+    assert st["last_path"] == (trx.PATH_UMMA if k <= 256 else trx.PATH_EXACT)
+
+
+def test_more_queries_than_one_batch():
+    """nq > max_batch: the call is cut into batches; every row of the output belongs to its query."""
+    trx = _engine()
+    n, d, nq, k = 30000, 64, 2500, 10
+    xb, xq = util.gaussian(n, d, 141), util.gaussian(nq, d, 142)
+    D, I, st = _run(xb, xq, k, IP, trx.PATH_AUTO, max_batch=1024)
+    Do, Io = oracle.search_blas(xb, xq, k, IP)
+    assert (I == Io).mean() > 0.999
+    oracle.check_parity(D[::50], I[::50], xb, xq[::50], k, IP)
+    oracle.check_parity(D[-3:], I[-3:], xb, xq[-3:], k, IP)
+
+
+def test_pipelined_batches_match_serial_batches():
+    """The double-buffered batch pipeline (upload / launch of batch i+1 overlapping batch i) returns exactly what
+    the serial loop returns, for pageable host arrays, pinned host arrays and device tensors, with a mask."""
+    import torch
+    trx = _engine()
+    n, d, nq, k = 30000, 64, 3000, 10
+    xb, xq = util.gaussian(n, d, 151), util.gaussian(nq, d, 152)
+    groups = (np.arange(n) // 3).astype(np.int32)
+    excl = groups[np.random.default_rng(153).integers(0, n, nq)].astype(np.int32)
+    idx = trx.IndexFlatIP(d)
+    idx.add(xb)
+    idx.set_groups(groups)
+    idx.set_option("max_batch", 512)
+    idx.set_option("target_candidates", 64)        # starve some lists: fallbacks inside the pipeline too
+    idx.set_option("pipeline", 0)
+    D0, I0 = idx.search(xq, k, exclude=excl)
+    assert idx.stats()["queries_exact"] > 0
+    idx.set_option("pipeline", 1)
+    D1, I1 = idx.search(xq, k, exclude=excl)                                    # pageable in / out
+    np.testing.assert_array_equal(I1, I0); np.testing.assert_array_equal(D1, D0)
+    hq = torch.from_numpy(xq).pin_memory()
+    hD = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    hI = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    idx.search(hq.numpy(), k, exclude=excl, D=hD.numpy(), I=hI.numpy())         # pinned in / out
+    np.testing.assert_array_equal(hI.numpy(), I0); np.testing.assert_array_equal(hD.numpy(), D0)
+    Dt, It = idx.search(torch.from_numpy(xq).cuda(), k, exclude=torch.from_numpy(excl).cuda())   # device in / out
+    np.testing.assert_array_equal(It.cpu().numpy(), I0); np.testing.assert_array_equal(Dt.cpu().numpy(), D0)
+    oracle.check_parity(D0[::40], I0[::40], xb, xq[::40], k, IP, groups, excl[::40])
+    idx.close()

@@ -86,6 +86,26 @@ __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t
 
 using namespace trx;
 
+// Everything one in-flight batch owns.  Two of them let batch i+1 be queued (queries uploaded on the copy
+// stream, kernels behind batch i on the compute stream) before the host waits for batch i.
+struct BatchWs {
+    int batch = 0, cap = 0, k = 0;                         // allocated for
+    float* q32 = nullptr; __nv_bfloat16* q16 = nullptr; float* qnorm2 = nullptr;
+    float* eps = nullptr; float* eps_acc = nullptr; float* thr = nullptr; int32_t* excl = nullptr;
+    Cand* cand = nullptr; uint32_t* cand_cnt = nullptr;
+    float* slots = nullptr; size_t slots_elems = 0;
+    HitRec* hitlog = nullptr; uint32_t* hitlog_cnt = nullptr; size_t hitlog_elems = 0; int hitlog_n = 0;
+    float* Dd = nullptr; int64_t* Id = nullptr;
+    int32_t* fb_list = nullptr; float* fb_thr = nullptr; uint32_t* fb_count = nullptr;
+    uint32_t* h_nfb = nullptr;                             // pinned: fallback count of this batch
+    float* hD = nullptr; int64_t* hI = nullptr; size_t h_elems = 0;   // pinned staging for pageable outputs
+    cudaEvent_t q_ready = nullptr, done = nullptr, ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // the batch in flight
+    int64_t B = 0; int path = 0;
+    const float* qdev = nullptr; const int32_t* exdev = nullptr;
+    float* D = nullptr; int64_t* I = nullptr; bool out_dev = false, out_pinned = false;
+};
+
 struct trx_index {
     int d = 0, metric = 0, device = 0, Kp = 0, sm_count = 148;
     int64_t ntotal = 0, capacity = 0, id_offset = 0;
@@ -107,33 +127,36 @@ struct trx_index {
     int timing = 0;
     int umma_pair = 1;      // allow the CTA-pair (cta_group::2) tiling
     int pair_min_batch = 129;  // ... for batches of at least this many queries (measured crossover)
+    int pipeline = 1;       // overlap the upload / launch of batch i+1 with batch i when a call has several
     float thr_bias = 0.f;   // experiments only: added to every estimated threshold
-    // workspaces (sized for max_batch)
-    int ws_batch = 0, ws_cap = 0;
-    float* q32 = nullptr; __nv_bfloat16* q16 = nullptr; float* qnorm2 = nullptr; float* eps = nullptr;
-    float* thr = nullptr; int32_t* excl = nullptr;
-    Cand* cand = nullptr; uint32_t* cand_cnt = nullptr;
-    float* slots = nullptr; size_t slots_elems = 0;
-    HitRec* hitlog = nullptr; uint32_t* hitlog_cnt = nullptr; size_t hitlog_elems = 0; int hitlog_n = 0;
-    float* Dd = nullptr; int64_t* Id = nullptr; int ws_k = 0;
-    int32_t* fb_list = nullptr; uint32_t* fb_count = nullptr; uint64_t* counters = nullptr;
-    float* fb_thr = nullptr; float* eps_acc = nullptr; float* neg_inf = nullptr;
-    int32_t* fb_list2 = nullptr; float* thr2 = nullptr;   // second-chance (threshold-guided) lists
+    BatchWs ws[2];
+    // fallback-only buffers (fallbacks run synchronously, one batch at a time)
+    int fb_batch = 0;
+    int32_t* fb_list2 = nullptr; float* thr2 = nullptr; float* neg_inf = nullptr;
     float* qfb = nullptr; int32_t* exfb = nullptr;
     float* xscores = nullptr; size_t xscores_elems = 0;  // exact-path score rows
-    uint32_t* h_nfb = nullptr;       // pinned: fallback count read back once per batch
-    cudaStream_t own_stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t* counters = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     trx_stats_t st{};
 };
 
+static void free_batch_ws(BatchWs& w) {
+    dfree(w.q32); dfree(w.q16); dfree(w.qnorm2); dfree(w.eps); dfree(w.eps_acc); dfree(w.thr); dfree(w.excl);
+    dfree(w.cand); dfree(w.cand_cnt); dfree(w.slots); dfree(w.hitlog); dfree(w.hitlog_cnt);
+    dfree(w.Dd); dfree(w.Id); dfree(w.fb_list); dfree(w.fb_thr); dfree(w.fb_count);
+    if (w.h_nfb) { cudaFreeHost(w.h_nfb); w.h_nfb = nullptr; }
+    if (w.hD) { cudaFreeHost(w.hD); w.hD = nullptr; }
+    if (w.hI) { cudaFreeHost(w.hI); w.hI = nullptr; }
+    if (w.q_ready) { cudaEventDestroy(w.q_ready); w.q_ready = nullptr; }
+    if (w.done) { cudaEventDestroy(w.done); w.done = nullptr; }
+    for (int i = 0; i < 4; i++) if (w.ev[i]) { cudaEventDestroy(w.ev[i]); w.ev[i] = nullptr; }
+    w.batch = w.cap = w.k = 0; w.slots_elems = w.hitlog_elems = w.h_elems = 0; w.hitlog_n = 0;
+}
+
 static void free_ws(trx_index* ix) {
-    dfree(ix->q32); dfree(ix->q16); dfree(ix->qnorm2); dfree(ix->eps); dfree(ix->thr); dfree(ix->excl);
-    dfree(ix->cand); dfree(ix->cand_cnt); dfree(ix->slots); dfree(ix->Dd); dfree(ix->Id);
-    dfree(ix->fb_list); dfree(ix->qfb); dfree(ix->exfb); dfree(ix->xscores);
-    dfree(ix->fb_thr); dfree(ix->eps_acc); dfree(ix->neg_inf); dfree(ix->fb_list2); dfree(ix->thr2);
-    dfree(ix->hitlog); dfree(ix->hitlog_cnt); ix->hitlog_elems = 0; ix->hitlog_n = 0;
-    ix->ws_batch = ix->ws_cap = ix->ws_k = 0; ix->slots_elems = 0; ix->xscores_elems = 0;
+    free_batch_ws(ix->ws[0]); free_batch_ws(ix->ws[1]);
+    dfree(ix->fb_list2); dfree(ix->thr2); dfree(ix->neg_inf); dfree(ix->qfb); dfree(ix->exfb); dfree(ix->xscores);
+    ix->fb_batch = 0; ix->xscores_elems = 0;
 }
 
 static void free_store(trx_index* ix) {
@@ -169,42 +192,53 @@ static int candidate_cap(const trx_index* ix, int k) {
     return p;
 }
 
-static int ensure_ws(trx_index* ix, int B, int k, int cap) {
-    if (B > ix->ws_batch || cap > ix->ws_cap) {
-        int nb = std::max(B, ix->ws_batch), nc = std::max(cap, ix->ws_cap);
-        dfree(ix->q32); dfree(ix->q16); dfree(ix->qnorm2); dfree(ix->eps); dfree(ix->thr); dfree(ix->excl);
-        dfree(ix->cand); dfree(ix->cand_cnt); dfree(ix->fb_list); dfree(ix->qfb); dfree(ix->exfb);
-        dfree(ix->fb_thr); dfree(ix->eps_acc); dfree(ix->neg_inf); dfree(ix->fb_list2); dfree(ix->thr2);
-        dfree(ix->Dd); dfree(ix->Id); ix->ws_k = 0;
-        TRX_TRY(dmalloc(&ix->q32, (size_t)nb * ix->d));
-        TRX_TRY(dmalloc(&ix->q16, (size_t)(nb + 8) * ix->Kp));   // K2 moves round8(nq) query rows
-        TRX_CUDA(cudaMemset(ix->q16, 0, (size_t)(nb + 8) * ix->Kp * 2));
-        TRX_TRY(dmalloc(&ix->qnorm2, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->eps, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->thr, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->excl, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->cand, (size_t)nb * nc));
-        TRX_TRY(dmalloc(&ix->cand_cnt, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->fb_list, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->qfb, (size_t)nb * ix->d));
-        TRX_TRY(dmalloc(&ix->exfb, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->fb_thr, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->eps_acc, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->neg_inf, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->fb_list2, (size_t)nb));
-        TRX_TRY(dmalloc(&ix->thr2, (size_t)nb));
-        {
-            std::vector<float> ninf((size_t)nb, -INFINITY);
-            TRX_CUDA(cudaMemcpy(ix->neg_inf, ninf.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
-        }
-        ix->ws_batch = nb; ix->ws_cap = nc;
+static int ensure_ws(trx_index* ix, BatchWs& w, int B, int k, int cap) {
+    if (!w.done) {
+        TRX_CUDA(cudaEventCreateWithFlags(&w.q_ready, cudaEventDisableTiming));
+        TRX_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+        for (int i = 0; i < 4; i++) TRX_CUDA(cudaEventCreate(&w.ev[i]));
+        TRX_CUDA(cudaHostAlloc((void**)&w.h_nfb, 64, cudaHostAllocDefault));
+        TRX_TRY(dmalloc(&w.fb_count, 1));
     }
-    if (k > ix->ws_k) {
-        dfree(ix->Dd); dfree(ix->Id);
-        TRX_TRY(dmalloc(&ix->Dd, (size_t)ix->ws_batch * k));
-        TRX_TRY(dmalloc(&ix->Id, (size_t)ix->ws_batch * k));
-        ix->ws_k = k;
+    if (B > w.batch || cap > w.cap) {
+        int nb = std::max(B, w.batch), nc = std::max(cap, w.cap);
+        dfree(w.q32); dfree(w.q16); dfree(w.qnorm2); dfree(w.eps); dfree(w.eps_acc); dfree(w.thr); dfree(w.excl);
+        dfree(w.cand); dfree(w.cand_cnt); dfree(w.fb_list); dfree(w.fb_thr);
+        dfree(w.Dd); dfree(w.Id); w.k = 0;
+        TRX_TRY(dmalloc(&w.q32, (size_t)nb * ix->d));
+        TRX_TRY(dmalloc(&w.q16, (size_t)(nb + 8) * ix->Kp));   // K2 moves round8(nq) query rows
+        TRX_CUDA(cudaMemset(w.q16, 0, (size_t)(nb + 8) * ix->Kp * 2));
+        TRX_TRY(dmalloc(&w.qnorm2, (size_t)nb));
+        TRX_TRY(dmalloc(&w.eps, (size_t)nb));
+        TRX_TRY(dmalloc(&w.eps_acc, (size_t)nb));
+        TRX_TRY(dmalloc(&w.thr, (size_t)nb));
+        TRX_TRY(dmalloc(&w.excl, (size_t)nb));
+        TRX_TRY(dmalloc(&w.cand, (size_t)nb * nc));
+        TRX_TRY(dmalloc(&w.cand_cnt, (size_t)nb));
+        TRX_TRY(dmalloc(&w.fb_list, (size_t)nb));
+        TRX_TRY(dmalloc(&w.fb_thr, (size_t)nb));
+        w.batch = nb; w.cap = nc;
     }
+    if (k > w.k) {
+        dfree(w.Dd); dfree(w.Id);
+        TRX_TRY(dmalloc(&w.Dd, (size_t)w.batch * k));
+        TRX_TRY(dmalloc(&w.Id, (size_t)w.batch * k));
+        w.k = k;
+    }
+    return TRX_OK;
+}
+
+static int ensure_fallback_ws(trx_index* ix, int B) {
+    if (B <= ix->fb_batch) return TRX_OK;
+    dfree(ix->fb_list2); dfree(ix->thr2); dfree(ix->neg_inf); dfree(ix->qfb); dfree(ix->exfb);
+    TRX_TRY(dmalloc(&ix->fb_list2, (size_t)B));
+    TRX_TRY(dmalloc(&ix->thr2, (size_t)B));
+    TRX_TRY(dmalloc(&ix->neg_inf, (size_t)B));
+    TRX_TRY(dmalloc(&ix->qfb, (size_t)B * ix->d));
+    TRX_TRY(dmalloc(&ix->exfb, (size_t)B));
+    std::vector<float> ninf((size_t)B, -INFINITY);
+    TRX_CUDA(cudaMemcpy(ix->neg_inf, ninf.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
+    ix->fb_batch = B;
     return TRX_OK;
 }
 
@@ -222,9 +256,9 @@ static int ensure_sample(trx_index* ix, cudaStream_t st) {
     return TRX_OK;
 }
 
-// exact path for nq queries whose fp32 rows are qdev[nq][d]; results to Dd/Id rows qmap[i] (or i).
+// exact path for nq queries whose fp32 rows are qdev[nq][d]; results to rows qmap[i] (or i) of Dd/Id.
 static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, const int32_t* qmap_dev, int64_t nq,
-                     int k, cudaStream_t st) {
+                     int k, float* Dd, int64_t* Id, cudaStream_t st) {
     const int64_t N = ix->ntotal;
     size_t budget = (size_t)64 << 20;  // floats (256 MB)
     int64_t rows = (int64_t)std::max<size_t>(8, std::min<size_t>(1024, budget / (size_t)N));
@@ -246,31 +280,81 @@ static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, 
         TRX_TRY(launch_stream(a, ix->sm_count, st));
         TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, k, ix->metric == TRX_METRIC_L2, ix->id_offset,
                                   qmap_dev ? qmap_dev + q0 : nullptr,
-                                  qmap_dev ? ix->Dd : ix->Dd + q0 * k, qmap_dev ? ix->Id : ix->Id + q0 * k, st));
+                                  qmap_dev ? Dd : Dd + q0 * k, qmap_dev ? Id : Id + q0 * k, st));
     }
     ix->st.queries_exact += nq;
     return TRX_OK;
 }
 
-static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, int k, const int32_t* excl,
+static bool is_pinned_host_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static RescoreArgs rescore_args(const trx_index* ix, const BatchWs& w, int k) {
+    RescoreArgs ra{};
+    ra.cand = w.cand; ra.cand_cnt = w.cand_cnt; ra.cap = w.cap; ra.thr = w.thr; ra.eps = w.eps;
+    ra.x32 = ix->x32; ra.d = ix->d; ra.n = ix->ntotal; ra.q32 = w.qdev; ra.nq = w.B;
+    ra.groups = ix->has_groups ? ix->groups : nullptr; ra.excl = w.exdev;
+    ra.k = k; ra.metric = ix->metric; ra.id_offset = ix->id_offset;
+    ra.D = w.Dd; ra.I = w.Id; ra.fb_list = w.fb_list; ra.fb_count = w.fb_count;
+    ra.fb_thr = w.fb_thr; ra.eps_acc = w.eps_acc; ra.qmap = nullptr; ra.counters = ix->counters;
+    return ra;
+}
+
+// results of batch w -> the caller's buffers (device: D2D; pinned host: D2H in place; pageable host: D2H into
+// pinned staging, copied out by finish_batch)
+static int send_results(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
+    const size_t n = (size_t)w.B * k;
+    if (w.out_dev || w.out_pinned) {
+        const cudaMemcpyKind kind = w.out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        TRX_CUDA(cudaMemcpyAsync(w.D, w.Dd, n * 4, kind, st));
+        TRX_CUDA(cudaMemcpyAsync(w.I, w.Id, n * 8, kind, st));
+    } else {
+        if (n > w.h_elems) {
+            if (w.hD) cudaFreeHost(w.hD);
+            if (w.hI) cudaFreeHost(w.hI);
+            w.hD = nullptr; w.hI = nullptr; w.h_elems = 0;
+            const size_t want = std::max(n, (size_t)w.batch * k);
+            TRX_CUDA(cudaHostAlloc((void**)&w.hD, want * 4, cudaHostAllocDefault));
+            TRX_CUDA(cudaHostAlloc((void**)&w.hI, want * 8, cudaHostAllocDefault));
+            w.h_elems = want;
+        }
+        TRX_CUDA(cudaMemcpyAsync(w.hD, w.Dd, n * 4, cudaMemcpyDeviceToHost, st));
+        TRX_CUDA(cudaMemcpyAsync(w.hI, w.Id, n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    return TRX_OK;
+}
+
+// Queue one batch: query upload (copy stream), every kernel, the fallback count and the results (compute
+// stream).  Nothing here waits for the GPU.
+static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev, int64_t B, int k, const int32_t* excl,
                         bool excl_dev, float* D, int64_t* I, bool out_dev, cudaStream_t st) {
     const int64_t N = ix->ntotal;
     const int cap = candidate_cap(ix, k);
-    TRX_TRY(ensure_ws(ix, (int)B, k, cap));
+    TRX_TRY(ensure_ws(ix, w, (int)B, k, cap));
+    w.B = B; w.D = D; w.I = I; w.out_dev = out_dev; w.out_pinned = !out_dev && is_pinned_host_ptr(D) && is_pinned_host_ptr(I);
 
-    // queries / exclusion list on the device
-    const float* qdev = xq;
+    // queries / exclusion list on the device: uploaded on the copy stream so that a (host-blocking) copy from
+    // pageable memory runs while the previous batch computes
+    w.qdev = xq;
+    w.exdev = nullptr;
+    bool uploaded = false;
     if (!xq_dev) {
-        TRX_CUDA(cudaMemcpyAsync(ix->q32, xq, (size_t)B * ix->d * 4, cudaMemcpyHostToDevice, st));
-        qdev = ix->q32;
+        TRX_CUDA(cudaMemcpyAsync(w.q32, xq, (size_t)B * ix->d * 4, cudaMemcpyHostToDevice, ix->copy_stream));
+        w.qdev = w.q32; uploaded = true;
     }
-    const int32_t* exdev = nullptr;
     if (excl && ix->has_groups) {
-        if (excl_dev) exdev = excl;
+        if (excl_dev) w.exdev = excl;
         else {
-            TRX_CUDA(cudaMemcpyAsync(ix->excl, excl, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-            exdev = ix->excl;
+            TRX_CUDA(cudaMemcpyAsync(w.excl, excl, (size_t)B * 4, cudaMemcpyHostToDevice, ix->copy_stream));
+            w.exdev = w.excl; uploaded = true;
         }
+    }
+    if (uploaded) {
+        TRX_CUDA(cudaEventRecord(w.q_ready, ix->copy_stream));
+        TRX_CUDA(cudaStreamWaitEvent(st, w.q_ready, 0));
     }
 
     int path = ix->opt_path;
@@ -281,164 +365,166 @@ static int search_batch(trx_index* ix, const float* xq, bool xq_dev, int64_t B, 
     } else if (path != TRX_PATH_EXACT && (N <= 2 * (int64_t)cap || k > 256)) {
         path = TRX_PATH_EXACT;  // prefilter needs a corpus larger than the candidate list
     }
+    w.path = path;
     ix->st.last_path = path;
-    bool results_sent = false;
-    if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[0], st));
+    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[0], st));
 
     if (path == TRX_PATH_EXACT) {
-        TRX_TRY(run_exact(ix, qdev, exdev, nullptr, B, k, st));
+        TRX_TRY(run_exact(ix, w.qdev, w.exdev, nullptr, B, k, w.Dd, w.Id, st));
+        *w.h_nfb = 0;
     } else {
         TRX_TRY(ensure_sample(ix, st));
-        TRX_TRY(launch_query_prep(qdev, B, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, ix->norm2_max, ix->eps,
-                                  ix->eps_acc, ix->cand_cnt, ix->fb_count, st));
+        TRX_TRY(launch_query_prep(w.qdev, B, ix->d, ix->Kp, ix->metric, w.q16, w.qnorm2, ix->norm2_max, w.eps,
+                                  w.eps_acc, w.cand_cnt, w.fb_count, st));
         const int T = std::max(ix->target, 4 * k);
         int r = std::max(1, (T + ix->sample_rate / 2) / ix->sample_rate);
 
         // pass 0 (both prefilter paths): tcgen05 scores of the batch against the 1/32 row sample, slot maxima,
         // r-th largest -> per-query threshold that ~T corpus rows are expected to beat
         UmmaArgs u{};
-        u.q16 = ix->q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
+        u.q16 = w.q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
         u.pair = ix->umma_pair && B >= ix->pair_min_batch;
         const int S = umma_num_slices(ix->ns, B, ix->sm_count, u.pair);
         size_t need = (size_t)B * S * 32;
-        if (need > ix->slots_elems) { dfree(ix->slots); TRX_TRY(dmalloc(&ix->slots, need)); ix->slots_elems = need; }
-        u.mode = 2; u.out = ix->slots;
+        if (need > w.slots_elems) { dfree(w.slots); TRX_TRY(dmalloc(&w.slots, need)); w.slots_elems = need; }
+        u.mode = 2; u.out = w.slots;
         TRX_TRY(launch_umma(u, ix->sm_count, st));
-        TRX_TRY(launch_slot_thr(ix->slots, B, S, std::min(r, 32 * S), ix->thr, st));
+        TRX_TRY(launch_slot_thr(w.slots, B, S, std::min(r, 32 * S), w.thr, st));
         if (ix->thr_bias != 0.f) {
-            add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(ix->thr, (int)B, ix->thr_bias);
+            add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.thr, (int)B, ix->thr_bias);
             count_launch();
         }
-        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[1], st));
+        if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[1], st));
 
         if (path == TRX_PATH_UMMA) {
             u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
-            u.thr = ix->thr; u.cand = ix->cand; u.cand_cnt = ix->cand_cnt; u.cap = cap;
+            u.thr = w.thr; u.cand = w.cand; u.cand_cnt = w.cand_cnt; u.cap = w.cap;
             {   // private hit logs: 3x the expected hits per epilogue thread, at least 256 entries
                 const int grid = umma_grid(B, N, ix->sm_count, u.pair, false);
                 const int nlogs = grid * 128;
                 double expect = 1.15 * (double)B * (double)T / (double)nlogs;
                 int log_cap = std::max(256, (int)(3.0 * expect) + 64);
                 size_t need_l = (size_t)nlogs * log_cap;
-                if (need_l > ix->hitlog_elems || nlogs > ix->hitlog_n) {
-                    dfree(ix->hitlog); dfree(ix->hitlog_cnt);
-                    TRX_TRY(dmalloc(&ix->hitlog, need_l));
-                    TRX_TRY(dmalloc(&ix->hitlog_cnt, (size_t)nlogs));
-                    ix->hitlog_elems = need_l; ix->hitlog_n = nlogs;
+                if (need_l > w.hitlog_elems || nlogs > w.hitlog_n) {
+                    dfree(w.hitlog); dfree(w.hitlog_cnt);
+                    TRX_TRY(dmalloc(&w.hitlog, need_l));
+                    TRX_TRY(dmalloc(&w.hitlog_cnt, (size_t)nlogs));
+                    w.hitlog_elems = need_l; w.hitlog_n = nlogs;
                 }
-                u.log = ix->hitlog; u.log_cnt = ix->hitlog_cnt; u.log_cap = log_cap;
+                u.log = w.hitlog; u.log_cnt = w.hitlog_cnt; u.log_cap = log_cap;
             }
             TRX_TRY(launch_umma(u, ix->sm_count, st));
         } else {
             // main pass on the CUDA cores: one sweep over the bf16 corpus per 4 queries, hits appended directly
             StreamArgs a{};
             a.x = ix->x16; a.pitch = ix->Kp; a.n = N; a.d = ix->Kp;
-            a.q16 = ix->q16; a.q_pitch = ix->Kp; a.nq = B;
+            a.q16 = w.q16; a.q_pitch = ix->Kp; a.nq = B;
             a.metric = TRX_METRIC_INNER_PRODUCT; a.bf16 = true; a.append = true;
-            a.thr = ix->thr; a.cand = ix->cand; a.cand_cnt = ix->cand_cnt; a.cap = cap;
+            a.thr = w.thr; a.cand = w.cand; a.cand_cnt = w.cand_cnt; a.cap = w.cap;
             TRX_TRY(launch_stream(a, ix->sm_count, st));
         }
-        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[2], st));
+        if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[2], st));
 
-        RescoreArgs ra{};
-        ra.cand = ix->cand; ra.cand_cnt = ix->cand_cnt; ra.cap = cap; ra.thr = ix->thr; ra.eps = ix->eps;
-        ra.x32 = ix->x32; ra.d = ix->d; ra.n = N; ra.q32 = qdev; ra.nq = B;
-        ra.groups = ix->has_groups ? ix->groups : nullptr; ra.excl = exdev;
-        ra.k = k; ra.metric = ix->metric; ra.id_offset = ix->id_offset;
-        ra.D = ix->Dd; ra.I = ix->Id; ra.fb_list = ix->fb_list; ra.fb_count = ix->fb_count;
-        ra.fb_thr = ix->fb_thr; ra.eps_acc = ix->eps_acc; ra.qmap = nullptr; ra.counters = ix->counters;
-        TRX_TRY(launch_rescore(ra, st));
-
-        // Common case (every query certified): the results leave with the same synchronisation that
-        // reads the fallback count.  Otherwise the fallback fills the missing rows and they are sent again.
-        TRX_CUDA(cudaMemcpyAsync(ix->h_nfb, ix->fb_count, 4, cudaMemcpyDeviceToHost, st));
-        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[3], st));
-        TRX_CUDA(cudaMemcpyAsync(D, ix->Dd, (size_t)B * k * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        TRX_CUDA(cudaMemcpyAsync(I, ix->Id, (size_t)B * k * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        TRX_CUDA(cudaStreamSynchronize(st));
-        const uint32_t nfb = *ix->h_nfb;
-        results_sent = nfb == 0;
-        if (nfb > 0) {
-            // Queries without a certificate.  Second chance, still exact: K4 left the k-th best exact
-            // score it saw; every true top-k row scores at least that, so one fp32 streaming pass
-            // that appends rows above it yields a short COMPLETE list, which K4 then finishes.
-            // Only queries with no usable bound (overflow / fewer than k candidates) take the
-            // generic scan + radix select.
-            std::vector<int32_t> h_list(nfb);
-            std::vector<float> h_thr(nfb);
-            TRX_CUDA(cudaMemcpyAsync(h_list.data(), ix->fb_list, (size_t)nfb * 4, cudaMemcpyDeviceToHost, st));
-            TRX_CUDA(cudaMemcpyAsync(h_thr.data(), ix->fb_thr, (size_t)nfb * 4, cudaMemcpyDeviceToHost, st));
-            TRX_CUDA(cudaStreamSynchronize(st));
-            std::vector<int32_t> lite, gen;
-            std::vector<float> lite_thr;
-            for (uint32_t i = 0; i < nfb; i++) {
-                if (h_thr[i] > -INFINITY) { lite.push_back(h_list[i]); lite_thr.push_back(h_thr[i]); }
-                else gen.push_back(h_list[i]);
-            }
-            if (!lite.empty()) {
-                const int nl = (int)lite.size();
-                TRX_CUDA(cudaMemcpyAsync(ix->fb_list2, lite.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
-                TRX_CUDA(cudaMemcpyAsync(ix->thr2, lite_thr.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
-                gather_rows_kernel<<<nl, 128, 0, st>>>(qdev, ix->fb_list2, ix->d, ix->qfb);
-                count_launch();
-                const int32_t* exfb = nullptr;
-                if (exdev) {
-                    gather_i32_kernel<<<(nl + 255) / 256, 256, 0, st>>>(exdev, ix->fb_list2, nl, ix->exfb);
-                    count_launch();
-                    exfb = ix->exfb;
-                }
-                TRX_CUDA(cudaGetLastError());
-                TRX_CUDA(cudaMemsetAsync(ix->cand_cnt, 0, (size_t)nl * 4, st));
-                TRX_CUDA(cudaMemsetAsync(ix->fb_count, 0, 4, st));
-                StreamArgs a{};
-                a.x = ix->x32; a.pitch = ix->d; a.n = N; a.d = ix->d;
-                a.q32 = ix->qfb; a.q_pitch = ix->d; a.nq = nl;
-                a.metric = ix->metric; a.bf16 = false; a.append = true;
-                a.thr = ix->thr2; a.cand = ix->cand; a.cand_cnt = ix->cand_cnt; a.cap = cap;
-                TRX_TRY(launch_stream(a, ix->sm_count, st));
-                RescoreArgs rb = ra;
-                rb.thr = ix->neg_inf;      // complete list: certified once everything is rescored
-                rb.q32 = ix->qfb; rb.nq = nl; rb.excl = exfb; rb.qmap = ix->fb_list2;
-                TRX_TRY(launch_rescore(rb, st));
-                uint32_t nfb2 = 0;
-                TRX_CUDA(cudaMemcpyAsync(&nfb2, ix->fb_count, 4, cudaMemcpyDeviceToHost, st));
-                TRX_CUDA(cudaStreamSynchronize(st));
-                if (nfb2 > 0) {
-                    size_t g0 = gen.size();
-                    gen.resize(g0 + nfb2);
-                    TRX_CUDA(cudaMemcpy(gen.data() + g0, ix->fb_list, (size_t)nfb2 * 4, cudaMemcpyDeviceToHost));
-                }
-                ix->st.queries_exact += nl - (int64_t)nfb2;
-            }
-            if (!gen.empty()) {
-                const int ng = (int)gen.size();
-                TRX_CUDA(cudaMemcpyAsync(ix->fb_list2, gen.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, st));
-                gather_rows_kernel<<<ng, 128, 0, st>>>(qdev, ix->fb_list2, ix->d, ix->qfb);
-                count_launch();
-                const int32_t* exfb = nullptr;
-                if (exdev) {
-                    gather_i32_kernel<<<(ng + 255) / 256, 256, 0, st>>>(exdev, ix->fb_list2, ng, ix->exfb);
-                    count_launch();
-                    exfb = ix->exfb;
-                }
-                TRX_CUDA(cudaGetLastError());
-                TRX_TRY(run_exact(ix, ix->qfb, exfb, ix->fb_list2, ng, k, st));
-                TRX_CUDA(cudaStreamSynchronize(st));   // `gen` (host) must outlive the async upload
-            }
-        }
+        TRX_TRY(launch_rescore(rescore_args(ix, w, k), st));
+        TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
     }
-    if (!results_sent) {
-        if (ix->timing) TRX_CUDA(cudaEventRecord(ix->ev[3], st));
-        TRX_CUDA(cudaMemcpyAsync(D, ix->Dd, (size_t)B * k * 4, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        TRX_CUDA(cudaMemcpyAsync(I, ix->Id, (size_t)B * k * 8, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        if (!out_dev || !xq_dev || ix->timing) TRX_CUDA(cudaStreamSynchronize(st));
+    // Common case (every query certified): the results leave with the same synchronisation that reads the
+    // fallback count.  Otherwise finish_batch fills the missing rows and sends them again.
+    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[3], st));
+    TRX_TRY(send_results(ix, w, k, st));
+    TRX_CUDA(cudaEventRecord(w.done, st));
+    return TRX_OK;
+}
+
+// Wait for batch w; run the exact fallbacks of the queries without a certificate; hand the results over.
+static int finish_batch(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
+    const int64_t N = ix->ntotal;
+    const int64_t B = w.B;
+    TRX_CUDA(cudaEventSynchronize(w.done));
+    const uint32_t nfb = w.path == TRX_PATH_EXACT ? 0u : *w.h_nfb;
+    if (nfb > 0) {
+        // Queries without a certificate.  Second chance, still exact: K4 left the k-th best exact
+        // score it saw; every true top-k row scores at least that, so one fp32 streaming pass
+        // that appends rows above it yields a short COMPLETE list, which K4 then finishes.
+        // Only queries with no usable bound (overflow / fewer than k candidates) take the
+        // generic scan + radix select.
+        TRX_TRY(ensure_fallback_ws(ix, w.batch));
+        std::vector<int32_t> h_list(nfb);
+        std::vector<float> h_thr(nfb);
+        TRX_CUDA(cudaMemcpyAsync(h_list.data(), w.fb_list, (size_t)nfb * 4, cudaMemcpyDeviceToHost, st));
+        TRX_CUDA(cudaMemcpyAsync(h_thr.data(), w.fb_thr, (size_t)nfb * 4, cudaMemcpyDeviceToHost, st));
+        TRX_CUDA(cudaStreamSynchronize(st));
+        std::vector<int32_t> lite, gen;
+        std::vector<float> lite_thr;
+        for (uint32_t i = 0; i < nfb; i++) {
+            if (h_thr[i] > -INFINITY) { lite.push_back(h_list[i]); lite_thr.push_back(h_thr[i]); }
+            else gen.push_back(h_list[i]);
+        }
+        if (!lite.empty()) {
+            const int nl = (int)lite.size();
+            TRX_CUDA(cudaMemcpyAsync(ix->fb_list2, lite.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+            TRX_CUDA(cudaMemcpyAsync(ix->thr2, lite_thr.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+            gather_rows_kernel<<<nl, 128, 0, st>>>(w.qdev, ix->fb_list2, ix->d, ix->qfb);
+            count_launch();
+            const int32_t* exfb = nullptr;
+            if (w.exdev) {
+                gather_i32_kernel<<<(nl + 255) / 256, 256, 0, st>>>(w.exdev, ix->fb_list2, nl, ix->exfb);
+                count_launch();
+                exfb = ix->exfb;
+            }
+            TRX_CUDA(cudaGetLastError());
+            TRX_CUDA(cudaMemsetAsync(w.cand_cnt, 0, (size_t)nl * 4, st));
+            TRX_CUDA(cudaMemsetAsync(w.fb_count, 0, 4, st));
+            StreamArgs a{};
+            a.x = ix->x32; a.pitch = ix->d; a.n = N; a.d = ix->d;
+            a.q32 = ix->qfb; a.q_pitch = ix->d; a.nq = nl;
+            a.metric = ix->metric; a.bf16 = false; a.append = true;
+            a.thr = ix->thr2; a.cand = w.cand; a.cand_cnt = w.cand_cnt; a.cap = w.cap;
+            TRX_TRY(launch_stream(a, ix->sm_count, st));
+            RescoreArgs rb = rescore_args(ix, w, k);
+            rb.thr = ix->neg_inf;      // complete list: certified once everything is rescored
+            rb.q32 = ix->qfb; rb.nq = nl; rb.excl = exfb; rb.qmap = ix->fb_list2;
+            TRX_TRY(launch_rescore(rb, st));
+            TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
+            TRX_CUDA(cudaStreamSynchronize(st));
+            const uint32_t nfb2 = *w.h_nfb;
+            if (nfb2 > 0) {
+                size_t g0 = gen.size();
+                gen.resize(g0 + nfb2);
+                TRX_CUDA(cudaMemcpy(gen.data() + g0, w.fb_list, (size_t)nfb2 * 4, cudaMemcpyDeviceToHost));
+            }
+            ix->st.queries_exact += nl - (int64_t)nfb2;
+        }
+        if (!gen.empty()) {
+            const int ng = (int)gen.size();
+            TRX_CUDA(cudaMemcpyAsync(ix->fb_list2, gen.data(), (size_t)ng * 4, cudaMemcpyHostToDevice, st));
+            gather_rows_kernel<<<ng, 128, 0, st>>>(w.qdev, ix->fb_list2, ix->d, ix->qfb);
+            count_launch();
+            const int32_t* exfb = nullptr;
+            if (w.exdev) {
+                gather_i32_kernel<<<(ng + 255) / 256, 256, 0, st>>>(w.exdev, ix->fb_list2, ng, ix->exfb);
+                count_launch();
+                exfb = ix->exfb;
+            }
+            TRX_CUDA(cudaGetLastError());
+            TRX_TRY(run_exact(ix, ix->qfb, exfb, ix->fb_list2, ng, k, w.Dd, w.Id, st));
+            TRX_CUDA(cudaStreamSynchronize(st));   // `gen` (host) must outlive the async upload
+        }
+        if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[3], st));
+        TRX_TRY(send_results(ix, w, k, st));
+        TRX_CUDA(cudaStreamSynchronize(st));
+    }
+    if (!w.out_dev && !w.out_pinned) {
+        memcpy(w.D, w.hD, (size_t)B * k * 4);
+        memcpy(w.I, w.hI, (size_t)B * k * 8);
     }
     if (ix->timing) {
         float ms = 0.f;
-        TRX_CUDA(cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]));
+        TRX_CUDA(cudaEventSynchronize(w.ev[3]));
+        TRX_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[3]));
         ix->st.last_total_ms = ms;
-        if (path != TRX_PATH_EXACT) {
-            TRX_CUDA(cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]));
+        if (w.path != TRX_PATH_EXACT) {
+            TRX_CUDA(cudaEventElapsedTime(&ms, w.ev[1], w.ev[2]));
             ix->st.last_prefilter_ms = ms;
         } else ix->st.last_prefilter_ms = 0.0;
     }
@@ -481,16 +567,13 @@ int trx_create(int d, int metric, int device, trx_index** out) {
     int rc = TRX_OK;
     do {
         if ((rc = dmalloc(&ix->norm2_max, 1)) != TRX_OK) break;
-        if ((rc = dmalloc(&ix->fb_count, 1)) != TRX_OK) break;
         if ((rc = dmalloc(&ix->counters, 4)) != TRX_OK) break;
         if (cudaMemset(ix->norm2_max, 0, 4) != cudaSuccess || cudaMemset(ix->counters, 0, 32) != cudaSuccess ||
-            cudaHostAlloc((void**)&ix->h_nfb, 64, cudaHostAllocDefault) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
             set_error("device init failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = TRX_ECUDA; break;
         }
-        for (int i = 0; i < 4; i++)
-            if (cudaEventCreate(&ix->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = TRX_ECUDA; break; }
     } while (0);
     if (rc != TRX_OK) { trx_destroy(ix); return rc; }
     ix->st.sm_count = ix->sm_count;
@@ -503,10 +586,9 @@ void trx_destroy(trx_index* ix) {
     DeviceGuard g(ix->device);
     cudaDeviceSynchronize();
     free_ws(ix); free_store(ix);
-    dfree(ix->norm2_max); dfree(ix->fb_count); dfree(ix->counters);
-    if (ix->h_nfb) { cudaFreeHost(ix->h_nfb); ix->h_nfb = nullptr; }
-    for (int i = 0; i < 4; i++) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+    dfree(ix->norm2_max); dfree(ix->counters);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+    if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
     delete ix;
 }
 
@@ -583,12 +665,25 @@ int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t*
         TRX_CUDA(cudaMemcpy(I, ifill.data(), ifill.size() * 8, out_dev ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
         return TRX_OK;
     }
-    for (int64_t q0 = 0; q0 < nq; q0 += ix->max_batch) {
-        int64_t B = std::min<int64_t>(ix->max_batch, nq - q0);
-        TRX_TRY(search_batch(ix, xq + q0 * ix->d, xq_dev, B, k, excl ? excl + q0 : nullptr, excl_dev, D + q0 * k,
-                             I + q0 * k, out_dev, st));
+    // Software pipeline over the batches of the call: batch i+1 is queued (upload on the copy stream, kernels
+    // behind batch i) before the host waits for batch i, so the GPU never idles between batches and host
+    // copies to / from pageable memory overlap compute.
+    const int64_t mb = ix->max_batch;
+    const int64_t nb = (nq + mb - 1) / mb;
+    auto launch = [&](int64_t i) {
+        const int64_t q0 = i * mb, B = std::min<int64_t>(mb, nq - q0);
+        return launch_batch(ix, ix->ws[i & 1], xq + q0 * ix->d, xq_dev, B, k, excl ? excl + q0 : nullptr, excl_dev,
+                            D + q0 * k, I + q0 * k, out_dev, st);
+    };
+    int rc = launch(0);
+    for (int64_t i = 0; rc == TRX_OK && i < nb; i++) {
+        if (ix->pipeline && i + 1 < nb) rc = launch(i + 1);
+        int rf = finish_batch(ix, ix->ws[i & 1], k, st);      // always drain what was queued
+        if (rc == TRX_OK) rc = rf;
+        if (rc == TRX_OK && !ix->pipeline && i + 1 < nb) rc = launch(i + 1);
     }
-    return TRX_OK;
+    if (rc != TRX_OK) cudaStreamSynchronize(st);
+    return rc;
 }
 
 int trx_set_option(trx_index* ix, const char* key, double v) {
@@ -609,6 +704,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->stream_max_batch = (int)v;
     } else if (!strcmp(key, "timing")) {
         ix->timing = v != 0;
+    } else if (!strcmp(key, "pipeline")) {
+        ix->pipeline = v != 0;
     } else if (!strcmp(key, "thr_bias")) {
         ix->thr_bias = (float)v;
     } else if (!strcmp(key, "umma_pair")) {
@@ -630,6 +727,7 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "timing")) *v = ix->timing;
     else if (!strcmp(key, "umma_pair")) *v = ix->umma_pair;
     else if (!strcmp(key, "pair_min_batch")) *v = ix->pair_min_batch;
+    else if (!strcmp(key, "pipeline")) *v = ix->pipeline;
     else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
@@ -662,11 +760,12 @@ int trx_debug_scores_umma(trx_index* ix, const float* xq, int64_t nq, int64_t ro
     if (!is_device_ptr(xq) || !is_device_ptr(out)) { set_error("debug_scores takes device pointers"); return TRX_EINVAL; }
     DeviceGuard g(ix->device);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
-    TRX_TRY(ensure_ws(ix, (int)nq, 1, candidate_cap(ix, 1)));
-    TRX_TRY(launch_query_prep(xq, nq, ix->d, ix->Kp, ix->metric, ix->q16, ix->qnorm2, nullptr, nullptr, nullptr, nullptr,
+    BatchWs& w = ix->ws[0];
+    TRX_TRY(ensure_ws(ix, w, (int)nq, 1, candidate_cap(ix, 1)));
+    TRX_TRY(launch_query_prep(xq, nq, ix->d, ix->Kp, ix->metric, w.q16, w.qnorm2, nullptr, nullptr, nullptr, nullptr,
                               nullptr, st));
     UmmaArgs u{};
-    u.q16 = ix->q16; u.nq = nq; u.x16 = ix->x16 + row0 * ix->Kp; u.n = n; u.Kp = ix->Kp;
+    u.q16 = w.q16; u.nq = nq; u.x16 = ix->x16 + row0 * ix->Kp; u.n = n; u.Kp = ix->Kp;
     u.mode = 0; u.out = out; u.out_ld = n;
     u.pair = ix->umma_pair && nq >= ix->pair_min_batch;
     TRX_TRY(launch_umma(u, ix->sm_count, st));
