@@ -11,6 +11,8 @@
  *   trx_search      <- index.search(query_fps, k)     retrieve/retrieve_faiss.py:71
  *   trx_set_groups  <- gold-removed mode, lifted from the consumer-side filter
  *                      `skip_gold_neighbor`           textreact/dataset.py:74-76
+ *   trx_set_row_attr <- `--before` year restriction         retrieve/retrieve_faiss.py:102-103
+ *   trx_search_self <- train->train search (queries are the corpus)  retrieve/retrieve_faiss.py:114-115
  *   trx_reset / trx_destroy <- lifetime of the index object built per split
  *                                                     retrieve/retrieve_faiss.py:62-74
  *   trx_merge_topk  <- (no reference counterpart) k-way merge of per-shard results for
@@ -81,16 +83,40 @@ int trx_create(int d, int metric, int device, trx_index** out);
 /* Append n rows of d floats (row-major, contiguous). */
 int trx_add(trx_index* idx, const float* x, int64_t n);
 
+/* Append n rows of d elements of type `dtype` (TRX_DTYPE_*), widened to fp32 on the device exactly as
+ * the FAISS python wrapper's np.ascontiguousarray(x, dtype='float32') would on the host: the reference
+ * passes int64 difference fingerprints and int8 Morgan bits (retrieve/retrieve_faiss.py:26, :40). */
+#define TRX_DTYPE_F32 0
+#define TRX_DTYPE_F64 1
+#define TRX_DTYPE_F16 2
+#define TRX_DTYPE_I8 3
+#define TRX_DTYPE_U8 4
+#define TRX_DTYPE_I16 5
+#define TRX_DTYPE_I32 6
+#define TRX_DTYPE_I64 7
+int trx_add_typed(trx_index* idx, const void* x, int64_t n, int dtype);
+
 /* Pre-size the device buffers for `n` total rows (optional; avoids regrowth copies). */
 int trx_reserve(trx_index* idx, int64_t n);
 
 /* Per-row exclusion group (text-dedup group / patent id), n must equal ntotal. */
 int trx_set_groups(trx_index* idx, const int32_t* g, int64_t n);
 
+/* Per-row integer attribute (e.g. the publication year: the reference restricts the corpus with
+ * `train_df[train_df['year'] < args.before]`, retrieve/retrieve_faiss.py:102-103, a dataframe filter before
+ * add).  With trx_set_option("attr_below", T) rows whose attribute is >= T are ineligible, so one resident
+ * corpus serves every --before split (retrieve/retro_year.sh:12).  n must equal ntotal; NULL clears. */
+int trx_set_row_attr(trx_index* idx, const int32_t* attr, int64_t n);
+
 /* k nearest rows for each of nq queries.  excl (nullable): per-query group to exclude,
  * -1 = none; requires trx_set_groups.  D: float[nq*k], I: int64[nq*k]. */
 int trx_search(trx_index* idx, const float* xq, int64_t nq, int k, const int32_t* excl,
                float* D, int64_t* I, void* cuda_stream);
+
+/* trx_search with the stored rows [row0, row0+nq) as the queries -- the reference's train->train search
+ * (query_fps is train_fps, retrieve/retrieve_faiss.py:114-115) without sending the corpus to the device twice. */
+int trx_search_self(trx_index* idx, int64_t row0, int64_t nq, int k, const int32_t* excl,
+                    float* D, int64_t* I, void* cuda_stream);
 
 /* Remove all rows (keeps d / metric / options). */
 int trx_reset(trx_index* idx);
@@ -106,7 +132,7 @@ int trx_set_id_offset(trx_index* idx, int64_t offset);
 /* Tunables: "path" (TRX_PATH_*), "max_batch", "target_candidates", "sample_rate",
  * "stream_max_batch" (crossover at or below which AUTO uses the streaming kernel),
  * "umma_pair" / "pair_min_batch" (CTA-pair tiling from this batch size on),
- * "pipeline" (0: serial batches), "timing". */
+ * "pipeline" (0: serial batches), "attr_below" (see trx_set_row_attr; 2147483647 = off), "timing". */
 int trx_set_option(trx_index* idx, const char* key, double value);
 int trx_get_option(const trx_index* idx, const char* key, double* value);
 

@@ -316,3 +316,76 @@ def test_pipelined_batches_match_serial_batches():
     np.testing.assert_array_equal(It.cpu().numpy(), I0); np.testing.assert_array_equal(Dt.cpu().numpy(), D0)
     oracle.check_parity(D0[::40], I0[::40], xb, xq[::40], k, IP, groups, excl[::40])
     idx.close()
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_search_self_equals_search_of_the_same_rows(metric):
+    """train->train mode (retrieve_faiss.py:114-115): queries are rows already in the index."""
+    trx = _engine()
+    xb = util.fingerprints(20000, 1024, 161) if metric == L2 else util.gaussian(20000, 256, 162)
+    idx = trx.IndexFlat(xb.shape[1], metric)
+    idx.add(xb)
+    D0, I0 = idx.search(xb[3000:3700], 20)
+    D1, I1 = idx.search_self(20, 3000, 3700)
+    np.testing.assert_array_equal(I1, I0); np.testing.assert_array_equal(D1, D0)
+    Dt, It = idx.search_self(20, 3000, 3700, device=True)
+    np.testing.assert_array_equal(It.cpu().numpy(), I0)
+    assert (I1[:, 0] == np.arange(3000, 3700)).all() or metric == L2     # L2 bits: duplicates may tie at distance 0
+    with pytest.raises(AssertionError):
+        idx.search_self(5, 10, 30000)
+    idx.close()
+
+
+@pytest.mark.parametrize("frac", [0.9, 0.5, 0.2, 0.04])
+@pytest.mark.parametrize("path_name", ["auto", "exact"])
+def test_row_attribute_filter_equals_filtered_corpus(frac, path_name):
+    """`--before T` (retrieve_faiss.py:102-103) as a per-row attribute: searching the full index with
+    attr_below=T equals searching an index built from the rows with year < T."""
+    trx = _engine()
+    n, d, nq, k = 50000, 128, 150, 20
+    xb, xq = util.gaussian(n, d, 171), util.gaussian(nq, d, 172)
+    years = np.random.default_rng(173).integers(1976, 2017, n).astype(np.int32)
+    T = int(np.quantile(years, frac))
+    keep = np.nonzero(years < T)[0]
+    idx = trx.IndexFlatIP(d)
+    idx.add(xb)
+    idx.set_row_attr(years)
+    if path_name == "exact":
+        idx.set_option("path", trx.PATH_EXACT)
+    D, I = idx.search(xq, k, attr_below=T)
+    assert (years[I] < T).all()
+    Do, Io = oracle.search_blas(xb[keep], xq, k, IP)
+    assert (I == keep[Io]).mean() > 0.999
+    oracle.check_parity(D[:40], np.searchsorted(keep, I[:40]), xb[keep], xq[:40], k, IP)
+    D2, I2 = idx.search(xq, k)                      # the filter is per call: off again
+    oracle.check_parity(D2[:20], I2[:20], xb, xq[:20], k, IP)
+    idx.close()
+
+
+@pytest.mark.parametrize("dtype", ["int8", "uint8", "bool", "int16", "int32", "int64", "float16", "float64"])
+def test_typed_add_equals_host_side_float32_coercion(dtype):
+    """index.add ships raw int8 / int64 / ... arrays and widens them on the device (trx_add_typed); the result
+    must be what FAISS's wrapper would have stored: np.ascontiguousarray(x, dtype='float32')."""
+    trx = _engine()
+    rng = np.random.default_rng(181)
+    n, d = 9000, 96
+    if dtype == "bool":
+        xb = rng.random((n, d)) < 0.1
+    elif dtype.startswith("float"):
+        xb = rng.standard_normal((n, d)).astype(dtype)
+    else:
+        lo = 0 if dtype == "uint8" else -3
+        xb = (rng.integers(lo, 4, (n, d)) * (rng.random((n, d)) < 0.2)).astype(dtype)
+    xq = np.ascontiguousarray(xb[:37], dtype=np.float32)
+    res = []
+    for arr in (xb, np.ascontiguousarray(xb, dtype=np.float32), np.asfortranarray(xb)):   # typed, fp32, non-contiguous
+        idx = trx.IndexFlatL2(d)
+        idx.add(arr[:5000]); idx.add(arr[5000:])
+        assert idx.ntotal == n
+        res.append(idx.search(xq, 10))
+        idx.close()
+    for D, I in res[1:]:
+        np.testing.assert_array_equal(I, res[0][1]); np.testing.assert_array_equal(D, res[0][0])
+    Do, Io = oracle.search_seq(xb, xq, 10, L2)
+    np.testing.assert_array_equal(res[0][1], Io)
+    np.testing.assert_allclose(res[0][0], Do, rtol=1e-6, atol=1e-6)

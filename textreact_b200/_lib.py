@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libtrx.so")
 
 TRX_OK, TRX_EINVAL, TRX_ENOMEM, TRX_ECUDA, TRX_ENODEV = 0, 1, 2, 3, 4
 PATH_AUTO, PATH_EXACT, PATH_STREAM, PATH_UMMA = 0, 1, 2, 3
+# TRX_DTYPE_* by numpy dtype name (trx_add_typed)
+DTYPES = {"float32": 0, "float64": 1, "float16": 2, "int8": 3, "uint8": 4, "bool": 4, "int16": 5, "int32": 6, "int64": 7}
 
 
 class TrxStats(ctypes.Structure):
@@ -33,9 +35,12 @@ _vp = ctypes.c_void_p
 SIGNATURES = {
     "trx_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
     "trx_add": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
+    "trx_add_typed": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int]),
     "trx_reserve": (ctypes.c_int, [_vp, ctypes.c_int64]),
     "trx_set_groups": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     "trx_search": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "trx_search_self": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "trx_set_row_attr": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     "trx_reset": (ctypes.c_int, [_vp]),
     "trx_destroy": (None, [_vp]),
     "trx_ntotal": (ctypes.c_int64, [_vp]),

@@ -73,6 +73,9 @@ struct __align__(16) HitRec {
 // squared norms, running max of the squared norm (as float bits).
 int launch_ingest(const float* x, int64_t n, int d, int Kp, int metric, __nv_bfloat16* x16,
                   float* xnorm2, uint32_t* norm2_max_bits, cudaStream_t st);
+// Raw typed array (TRX_DTYPE_*) -> fp32, elementwise, on the device (same values as numpy's astype(float32)).
+int launch_widen(const void* src, int dtype, int64_t count, float* dst, cudaStream_t st);
+int dtype_size(int dtype);  // bytes per element, 0 for an unknown code
 // One pseudo-randomly chosen row out of every `rate` consecutive rows -> xs16 [ns, Kp].
 int launch_sample_gather(const __nv_bfloat16* x16, int64_t n, int Kp, int rate, __nv_bfloat16* xs16,
                          int64_t ns, cudaStream_t st);
@@ -91,6 +94,7 @@ struct StreamArgs {
     const void* x; int64_t pitch; int64_t n; int d;   // d = number of columns to reduce over
     const float* q32; const __nv_bfloat16* q16; int64_t q_pitch; int64_t nq;
     const int32_t* groups; const int32_t* excl;
+    const int32_t* attr; int32_t attr_below;          // scores mode: rows with attr >= attr_below are ineligible
     float* out; int64_t out_ld;                       // scores mode
     const float* thr; Cand* cand; uint32_t* cand_cnt; int cap;  // append mode
     int metric; bool bf16; bool append;
@@ -116,6 +120,7 @@ struct RescoreArgs {
     const float* x32; int d; int64_t n;
     const float* q32; int64_t nq;
     const int32_t* groups; const int32_t* excl;
+    const int32_t* attr; int32_t attr_below;   // nullable: rows with attr[row] >= attr_below are ineligible
     int k; int metric; int64_t id_offset;
     float* D; int64_t* I;
     int32_t* fb_list; uint32_t* fb_count;  // queries that need the exact scan

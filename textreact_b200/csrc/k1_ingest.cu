@@ -3,6 +3,8 @@
 // Replaces the storage half of faiss `index.add(train_fps)` (retrieve/retrieve_faiss.py:66):
 // FAISS keeps one fp32 row-major copy; we keep that copy (for the exact rescore) plus a bf16
 // copy laid out for TMA (row pitch Kp, a multiple of 64 elements = one 128-byte swizzle row).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace trx {
@@ -70,6 +72,51 @@ __global__ void __launch_bounds__(256) k1_ingest_kernel(const float* __restrict_
         }
     }
     if (lane == 0 && wmax > 0.f) atomicMax(norm2_max_bits, __float_as_uint(wmax));  // >= 0: bit order == value order
+}
+
+// Typed ingestion: the reference hands FAISS int8 Morgan bits and int64 difference counts
+// (retrieve/retrieve_faiss.py:26, :40) and FAISS's wrapper converts them to fp32 on the host; here the raw
+// array crosses PCIe as it is and is widened on the device.
+template <typename T>
+__global__ void __launch_bounds__(256) k1_widen_kernel(const T* __restrict__ src, int64_t count, float* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = (float)src[i];
+}
+template <>
+__global__ void __launch_bounds__(256) k1_widen_kernel<__half>(const __half* __restrict__ src, int64_t count,
+                                                                float* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = __half2float(src[i]);
+}
+
+int dtype_size(int dtype) {
+    switch (dtype) {
+        case TRX_DTYPE_F32: case TRX_DTYPE_I32: return 4;
+        case TRX_DTYPE_F64: case TRX_DTYPE_I64: return 8;
+        case TRX_DTYPE_F16: case TRX_DTYPE_I16: return 2;
+        case TRX_DTYPE_I8: case TRX_DTYPE_U8: return 1;
+    }
+    return 0;
+}
+
+int launch_widen(const void* src, int dtype, int64_t count, float* dst, cudaStream_t st) {
+    if (count <= 0) return TRX_OK;
+    int64_t blocks = (count + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    const unsigned g = (unsigned)blocks;
+    switch (dtype) {
+        case TRX_DTYPE_F64: k1_widen_kernel<double><<<g, 256, 0, st>>>((const double*)src, count, dst); break;
+        case TRX_DTYPE_F16: k1_widen_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, count, dst); break;
+        case TRX_DTYPE_I8: k1_widen_kernel<int8_t><<<g, 256, 0, st>>>((const int8_t*)src, count, dst); break;
+        case TRX_DTYPE_U8: k1_widen_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)src, count, dst); break;
+        case TRX_DTYPE_I16: k1_widen_kernel<int16_t><<<g, 256, 0, st>>>((const int16_t*)src, count, dst); break;
+        case TRX_DTYPE_I32: k1_widen_kernel<int32_t><<<g, 256, 0, st>>>((const int32_t*)src, count, dst); break;
+        case TRX_DTYPE_I64: k1_widen_kernel<long long><<<g, 256, 0, st>>>((const long long*)src, count, dst); break;
+        default: set_error("widen: bad dtype %d", dtype); return TRX_EINVAL;
+    }
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
 }
 
 int launch_ingest(const float* x, int64_t n, int d, int Kp, int metric, __nv_bfloat16* x16, float* xnorm2,

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(256) k3_stream_kernel(StreamArgs a, int64_t q0
                 } else {
                     const int32_t ex = s_ex[q];
                     if (ex >= 0 && __ldg(a.groups + row) == ex) s = -INFINITY;
+                    if (a.attr != nullptr && __ldg(a.attr + row) >= a.attr_below) s = -INFINITY;
                     a.out[(q0 + q) * a.out_ld + row] = s;
                 }
             }

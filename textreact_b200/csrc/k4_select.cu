@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
         if (i < n_c) {
             Cand c = a.cand[q * (int64_t)a.cap + i];
             bool ok = !(ex >= 0 && __ldg(a.groups + c.row) == ex);
+            if (a.attr != nullptr && __ldg(a.attr + c.row) >= a.attr_below) ok = false;
             if (ok) { key = pack_key(c.score, (uint32_t)c.row); my_valid++; }
         }
         keys[i] = key;

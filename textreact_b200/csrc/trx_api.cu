@@ -12,6 +12,7 @@
 //
 // The fallback is an exact GPU path, not a CPU one: nothing here ever computes on the host.
 #include <float.h>
+#include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -114,6 +115,10 @@ struct trx_index {
     float* xnorm2 = nullptr;         // [capacity]
     int32_t* groups = nullptr;       // [capacity] (valid when has_groups)
     bool has_groups = false;
+    int32_t* attr = nullptr;         // [ntotal] per-row attribute (e.g. year), valid when has_attr
+    bool has_attr = false;
+    int32_t attr_below = INT32_MAX;  // rows with attr >= attr_below are ineligible (INT32_MAX: no filter)
+    std::vector<int32_t> attr_sorted; // host copy, sorted: eligible fraction of a bound in O(log N)
     uint32_t* norm2_max = nullptr;   // 1 (float bits)
     // 1/rate row sample for threshold estimation
     __nv_bfloat16* xs16 = nullptr; int64_t ns = 0, ns_cap = 0; bool sample_dirty = true;
@@ -160,8 +165,9 @@ static void free_ws(trx_index* ix) {
 }
 
 static void free_store(trx_index* ix) {
-    dfree(ix->x32); dfree(ix->x16); dfree(ix->xnorm2); dfree(ix->groups); dfree(ix->xs16);
+    dfree(ix->x32); dfree(ix->x16); dfree(ix->xnorm2); dfree(ix->groups); dfree(ix->xs16); dfree(ix->attr);
     ix->capacity = 0; ix->ntotal = 0; ix->ns = ix->ns_cap = 0; ix->has_groups = false; ix->sample_dirty = true;
+    ix->has_attr = false; ix->attr_sorted.clear();
 }
 
 static int grow(trx_index* ix, int64_t need) {
@@ -184,8 +190,26 @@ static int grow(trx_index* ix, int64_t need) {
     return TRX_OK;
 }
 
-static int candidate_cap(const trx_index* ix, int k) {
+static bool attr_active(const trx_index* ix) { return ix->has_attr && ix->attr_below != INT32_MAX; }
+
+// fraction of rows that pass the attribute filter
+static double eligible_fraction(const trx_index* ix) {
+    if (!attr_active(ix) || ix->attr_sorted.empty()) return 1.0;
+    auto it = std::lower_bound(ix->attr_sorted.begin(), ix->attr_sorted.end(), ix->attr_below);
+    return (double)(it - ix->attr_sorted.begin()) / (double)ix->attr_sorted.size();
+}
+
+// Candidates per query the prefilter aims for.  The threshold is sized on ALL rows; with an attribute filter
+// only a fraction f of the candidates is eligible, so the target grows by 1/f (bounded by K4's list size).
+static int effective_target(const trx_index* ix, int k) {
     int T = std::max(ix->target, 4 * k);
+    const double f = eligible_fraction(ix);
+    if (f < 1.0) T = (int)std::min<double>(2048.0, std::ceil(T / std::max(f, 1e-6)));
+    return T;
+}
+
+static int candidate_cap(const trx_index* ix, int k) {
+    int T = effective_target(ix, k);
     int cap = 4 * T;
     int p = 1024;
     while (p < cap) p <<= 1;
@@ -275,6 +299,7 @@ static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, 
         a.q32 = qdev + q0 * ix->d; a.q_pitch = ix->d; a.nq = nb;
         a.groups = ix->has_groups ? ix->groups : nullptr;
         a.excl = (excl_dev && ix->has_groups) ? excl_dev + q0 : nullptr;
+        a.attr = attr_active(ix) ? ix->attr : nullptr; a.attr_below = ix->attr_below;
         a.out = ix->xscores; a.out_ld = N;
         a.metric = ix->metric; a.bf16 = false; a.append = false;
         TRX_TRY(launch_stream(a, ix->sm_count, st));
@@ -297,6 +322,7 @@ static RescoreArgs rescore_args(const trx_index* ix, const BatchWs& w, int k) {
     ra.cand = w.cand; ra.cand_cnt = w.cand_cnt; ra.cap = w.cap; ra.thr = w.thr; ra.eps = w.eps;
     ra.x32 = ix->x32; ra.d = ix->d; ra.n = ix->ntotal; ra.q32 = w.qdev; ra.nq = w.B;
     ra.groups = ix->has_groups ? ix->groups : nullptr; ra.excl = w.exdev;
+    ra.attr = attr_active(ix) ? ix->attr : nullptr; ra.attr_below = ix->attr_below;
     ra.k = k; ra.metric = ix->metric; ra.id_offset = ix->id_offset;
     ra.D = w.Dd; ra.I = w.Id; ra.fb_list = w.fb_list; ra.fb_count = w.fb_count;
     ra.fb_thr = w.fb_thr; ra.eps_acc = w.eps_acc; ra.qmap = nullptr; ra.counters = ix->counters;
@@ -365,6 +391,9 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
     } else if (path != TRX_PATH_EXACT && (N <= 2 * (int64_t)cap || k > 256)) {
         path = TRX_PATH_EXACT;  // prefilter needs a corpus larger than the candidate list
     }
+    // a filter that keeps less than ~1/8 of the rows would starve the candidate lists: scan exactly instead
+    if (path != TRX_PATH_EXACT && eligible_fraction(ix) * 2048.0 < (double)std::max(ix->target, 4 * k) * 0.33)
+        path = TRX_PATH_EXACT;
     w.path = path;
     ix->st.last_path = path;
     if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[0], st));
@@ -376,7 +405,7 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
         TRX_TRY(ensure_sample(ix, st));
         TRX_TRY(launch_query_prep(w.qdev, B, ix->d, ix->Kp, ix->metric, w.q16, w.qnorm2, ix->norm2_max, w.eps,
                                   w.eps_acc, w.cand_cnt, w.fb_count, st));
-        const int T = std::max(ix->target, 4 * k);
+        const int T = effective_target(ix, k);
         int r = std::max(1, (T + ix->sample_rate / 2) / ix->sample_rate);
 
         // pass 0 (both prefilter paths): tcgen05 scores of the batch against the 1/32 row sample, slot maxima,
@@ -624,7 +653,53 @@ int trx_add(trx_index* ix, const float* x, int64_t n) {
     TRX_CUDA(cudaStreamSynchronize(st));
     ix->ntotal += n;
     ix->sample_dirty = true;
-    ix->has_groups = false;  // groups must cover every row: set them again after the last add
+    ix->has_groups = false;  // groups / attributes must cover every row: set them again after the last add
+    ix->has_attr = false;
+    return TRX_OK;
+}
+
+int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
+    if (dtype == TRX_DTYPE_F32) return trx_add(ix, (const float*)x, n);
+    if (!ix || n < 0 || (n > 0 && !x)) { set_error("bad argument"); return TRX_EINVAL; }
+    const int es = dtype_size(dtype);
+    if (es == 0) { set_error("add_typed: unknown dtype %d", dtype); return TRX_EINVAL; }
+    if (n == 0) return TRX_OK;
+    DeviceGuard g(ix->device);
+    TRX_TRY(grow(ix, ix->ntotal + n));
+    cudaStream_t st = ix->own_stream;
+    const bool dev = is_device_ptr(x);
+    // raw rows cross PCIe in chunks of <= 256 MB through one staging buffer, widened straight into the fp32 store
+    const int64_t rows_per_chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)ix->d * es));
+    void* stage = nullptr;
+    if (!dev) {
+        cudaError_t e = cudaMalloc(&stage, (size_t)std::min(rows_per_chunk, n) * ix->d * es);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of the ingest staging buffer failed"); return TRX_ENOMEM; }
+    }
+    int rc = TRX_OK;
+    for (int64_t r0 = 0; r0 < n && rc == TRX_OK; r0 += rows_per_chunk) {
+        const int64_t nr = std::min(rows_per_chunk, n - r0);
+        const char* src = (const char*)x + (size_t)r0 * ix->d * es;
+        const void* dsrc = src;
+        if (!dev) {
+            if (cudaMemcpyAsync(stage, src, (size_t)nr * ix->d * es, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+                set_error("add_typed: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = TRX_ECUDA; break;
+            }
+            dsrc = stage;
+        }
+        float* dst = ix->x32 + (ix->ntotal + r0) * ix->d;
+        rc = launch_widen(dsrc, dtype, nr * ix->d, dst, st);
+        if (rc == TRX_OK)
+            rc = launch_ingest(dst, nr, ix->d, ix->Kp, ix->metric, ix->x16 + (ix->ntotal + r0) * ix->Kp,
+                               ix->xnorm2 + ix->ntotal + r0, ix->norm2_max, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (stage) cudaFree(stage);
+    if (rc != TRX_OK) return rc;
+    if (e != cudaSuccess) { set_error("add_typed: %s", cudaGetErrorString(e)); return TRX_ECUDA; }
+    ix->ntotal += n;
+    ix->sample_dirty = true;
+    ix->has_groups = false;
+    ix->has_attr = false;
     return TRX_OK;
 }
 
@@ -637,6 +712,35 @@ int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
     TRX_CUDA(cudaMemcpy(ix->groups, gsrc, (size_t)n * 4, is_device_ptr(gsrc) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     ix->has_groups = true;
     return TRX_OK;
+}
+
+int trx_set_row_attr(trx_index* ix, const int32_t* asrc, int64_t n) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    if (asrc == nullptr) { ix->has_attr = false; ix->attr_sorted.clear(); return TRX_OK; }
+    if (n != ix->ntotal) { set_error("set_row_attr: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
+    if (n == 0) return TRX_OK;
+    DeviceGuard g(ix->device);
+    dfree(ix->attr);
+    TRX_TRY(dmalloc(&ix->attr, (size_t)n));
+    const bool dev = is_device_ptr(asrc);
+    TRX_CUDA(cudaMemcpy(ix->attr, asrc, (size_t)n * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    try { ix->attr_sorted.resize((size_t)n); } catch (...) { set_error("host allocation failed"); return TRX_ENOMEM; }
+    if (dev) TRX_CUDA(cudaMemcpy(ix->attr_sorted.data(), asrc, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    else memcpy(ix->attr_sorted.data(), asrc, (size_t)n * 4);
+    std::sort(ix->attr_sorted.begin(), ix->attr_sorted.end());
+    ix->has_attr = true;
+    return TRX_OK;
+}
+
+int trx_search_self(trx_index* ix, int64_t row0, int64_t nq, int k, const int32_t* excl, float* D, int64_t* I,
+                    void* cuda_stream) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    if (row0 < 0 || nq < 0 || row0 + nq > ix->ntotal) {
+        set_error("search_self: rows [%lld, %lld) outside [0, %lld)", (long long)row0, (long long)(row0 + nq), (long long)ix->ntotal);
+        return TRX_EINVAL;
+    }
+    if (nq == 0) return TRX_OK;
+    return trx_search(ix, ix->x32 + row0 * ix->d, nq, k, excl, D, I, cuda_stream);
 }
 
 int trx_set_id_offset(trx_index* ix, int64_t offset) {
@@ -706,6 +810,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->timing = v != 0;
     } else if (!strcmp(key, "pipeline")) {
         ix->pipeline = v != 0;
+    } else if (!strcmp(key, "attr_below")) {
+        ix->attr_below = v >= 2147483647.0 ? INT32_MAX : (v <= -2147483648.0 ? INT32_MIN : (int32_t)v);
     } else if (!strcmp(key, "thr_bias")) {
         ix->thr_bias = (float)v;
     } else if (!strcmp(key, "umma_pair")) {
@@ -728,6 +834,7 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "umma_pair")) *v = ix->umma_pair;
     else if (!strcmp(key, "pair_min_batch")) *v = ix->pair_min_batch;
     else if (!strcmp(key, "pipeline")) *v = ix->pipeline;
+    else if (!strcmp(key, "attr_below")) *v = ix->attr_below;
     else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }

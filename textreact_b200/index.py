@@ -13,7 +13,8 @@ passes int64 difference fingerprints (:26) and int8 Morgan bits (:40).  A wrong 
 dimension raises ``AssertionError`` (FAISS behaviour); engine failures raise ``RuntimeError``
 / ``MemoryError``.  Extensions, all keyword-only and ignored by the reference script:
 ``exclude=`` (gold-removed mode, textreact/dataset.py:74-76 lifted into the engine),
-``set_groups``, torch CUDA tensors in / out, ``device=``.
+``set_groups``, ``set_row_attr`` / ``attr_below=`` (the ``--before`` year restriction, :102-103),
+``search_self`` (train->train search, :114-115), torch CUDA tensors in / out, ``device=``.
 """
 from __future__ import annotations
 
@@ -93,15 +94,36 @@ class IndexFlat:
 
     # -- FAISS methods ----------------------------------------------------------------------
     def add(self, x):
+        if isinstance(x, np.ndarray) and x.dtype.name in _lib.DTYPES and x.dtype != np.float32 and x.ndim == 2 \
+                and x.flags.c_contiguous:
+            # int8 Morgan bits / int64 difference counts (retrieve_faiss.py:26, :40): ship the raw array,
+            # widen on the device -- same values as FAISS's np.ascontiguousarray(x, dtype='float32')
+            assert x.shape[1] == self.d, f"expected shape [n, {self.d}], got {x.shape}"
+            _lib.check(self._L.trx_add_typed(self._h, x.ctypes.data, x.shape[0], _lib.DTYPES[x.dtype.name]), "add")
+            return
         ptr, n, keep, on_dev = _as_f32_matrix(x, self.d)
         if on_dev:   # trx_add copies on the index's own stream: the producer of `x` must have finished
             torch.cuda.current_stream(keep.device).synchronize()
         _lib.check(self._L.trx_add(self._h, ptr, n), "add")
         del keep
 
-    def search(self, x, k, *, D=None, I=None, exclude=None, params=None):
+    def search(self, x, k, *, D=None, I=None, exclude=None, attr_below=None, params=None):
         assert k > 0
         ptr, nq, keep, on_dev = _as_f32_matrix(x, self.d)
+        return self._search(ptr, nq, keep, on_dev, k, D, I, exclude, attr_below, None)
+
+    def search_self(self, k, start=0, stop=None, *, D=None, I=None, exclude=None, attr_below=None, device=False):
+        """``search(xb[start:stop], k)`` with the rows already stored in the index as the queries -- the
+        reference's train->train search (retrieve/retrieve_faiss.py:114-115, ``query_fps = train_fps``)
+        without sending the corpus to the GPU a second time.  numpy out unless ``device=True``."""
+        assert k > 0
+        stop = self.ntotal if stop is None else int(stop)
+        start = int(start)
+        assert 0 <= start <= stop <= self.ntotal, f"rows [{start}, {stop}) outside [0, {self.ntotal})"
+        keep = torch.empty(0, device=torch.device("cuda", self.device)) if device else None
+        return self._search(None, stop - start, keep, bool(device), k, D, I, exclude, attr_below, start)
+
+    def _search(self, ptr, nq, keep, on_dev, k, D, I, exclude, attr_below, self_row0):
         ex_ptr, ex_keep = (None, None)
         if exclude is not None:
             ex_ptr, ex_keep = _as_i32_vector(exclude, nq, "exclude")
@@ -122,7 +144,17 @@ class IndexFlat:
             assert Dn.flags.c_contiguous and In.flags.c_contiguous
             dptr, iptr = Dn.ctypes.data, In.ctypes.data
             out = (Dn, In)
-        _lib.check(self._L.trx_search(self._h, ptr, nq, int(k), ex_ptr, dptr, iptr, stream), "search")
+        if attr_below is not None:
+            self.set_option("attr_below", attr_below)
+        try:
+            if self_row0 is None:
+                _lib.check(self._L.trx_search(self._h, ptr, nq, int(k), ex_ptr, dptr, iptr, stream), "search")
+            else:
+                _lib.check(self._L.trx_search_self(self._h, self_row0, nq, int(k), ex_ptr, dptr, iptr, stream),
+                           "search_self")
+        finally:
+            if attr_below is not None:
+                self.set_option("attr_below", 2147483647)
         del keep, ex_keep
         return out
 
@@ -142,6 +174,19 @@ class IndexFlat:
         if _is_torch(keep) and keep.is_cuda:
             torch.cuda.current_stream(keep.device).synchronize()
         _lib.check(self._L.trx_set_groups(self._h, ptr, self.ntotal), "set_groups")
+        del keep
+
+    def set_row_attr(self, attr):
+        """Per-row integer attribute (e.g. year), one int32 per added row; ``search(..., attr_below=T)``
+        then only returns rows with attr < T -- the ``--before`` restriction of
+        retrieve/retrieve_faiss.py:102-103 without rebuilding the index per split."""
+        if attr is None:
+            _lib.check(self._L.trx_set_row_attr(self._h, None, 0), "set_row_attr")
+            return
+        ptr, keep = _as_i32_vector(attr, self.ntotal, "attr")
+        if _is_torch(keep) and keep.is_cuda:
+            torch.cuda.current_stream(keep.device).synchronize()
+        _lib.check(self._L.trx_set_row_attr(self._h, ptr, self.ntotal), "set_row_attr")
         del keep
 
     def set_id_offset(self, offset):

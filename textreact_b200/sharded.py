@@ -57,7 +57,11 @@ class ShardedIndexFlat:
         lo, hi = self._lo, self._lo + self.local.ntotal
         self.local.set_groups(groups[lo:hi])
 
-    def search(self, xq, k, *, exclude=None):
+    def set_row_attr_global(self, attr):
+        lo, hi = self._lo, self._lo + self.local.ntotal
+        self.local.set_row_attr(attr[lo:hi])
+
+    def search(self, xq, k, *, exclude=None, attr_below=None):
         """xq replicated on every rank.  Returns (D, I) on every rank (numpy in -> numpy out)."""
         as_numpy = not (isinstance(xq, torch.Tensor) and xq.is_cuda)
         if as_numpy and self._on_cuda:
@@ -68,7 +72,8 @@ class ShardedIndexFlat:
             xq = torch.from_numpy(np.ascontiguousarray(xq, dtype=np.float32)).to(dev)
             if exclude is not None and not (isinstance(exclude, torch.Tensor) and exclude.is_cuda):
                 exclude = torch.as_tensor(np.ascontiguousarray(exclude, dtype=np.int32)).to(dev)
-        D, I = self.local.search(xq, k, exclude=exclude)
+        kw = {} if attr_below is None else {"attr_below": attr_below}
+        D, I = self.local.search(xq, k, exclude=exclude, **kw)
         if not isinstance(D, torch.Tensor):
             D, I = torch.from_numpy(D), torch.from_numpy(I)
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
