@@ -388,4 +388,4 @@ def test_typed_add_equals_host_side_float32_coercion(dtype):
         np.testing.assert_array_equal(I, res[0][1]); np.testing.assert_array_equal(D, res[0][0])
     Do, Io = oracle.search_seq(xb, xq, 10, L2)
     np.testing.assert_array_equal(res[0][1], Io)
-    np.testing.assert_allclose(res[0][0], Do, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(res[0][0], Do, rtol=1e-5, atol=1e-5)
