@@ -166,7 +166,7 @@ def run_reference(args):
            "config": {"workload": name, "rows": rows, "batch": batch, "k": K, "d": D_MODEL},
            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def stage(msg):
@@ -178,6 +178,15 @@ def stage(msg):
 
 
 T_START = time.perf_counter()
+# Only the JSON line goes to the real stdout: libraries (NCCL prints its version there when NCCL_DEBUG is
+# VERSION/WARN) are pointed at stderr for the whole run.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
@@ -378,7 +387,7 @@ def main():
                "cpu_baseline": cpu,
                "engine": {k: st[k] for k in ("queries", "queries_exact", "queries_uncert", "queries_overflow",
                                              "rescored", "candidates", "last_path")}}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
