@@ -343,6 +343,24 @@ def main():
     local.set_option("timing", 0)
     st = local.stats()
     pk = peaks()
+
+    # ---- multi-GPU: where the step goes -- per-rank local search time, and the exchange (all-gather + K5) alone
+    multi = None
+    if world > 1:
+        mine = torch.tensor([sum(tot_ms) / len(tot_ms), sum(pre_ms) / len(pre_ms)], device=dev)
+        allr = torch.empty((world, 2), device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        Dl, Il = local.search(queries[0], K)
+
+        def exchange(i):
+            sidx.exchange(Dl, Il)
+        for i in range(3):
+            exchange(i)
+        ex_ms = timed(exchange, 10) / 10
+        multi = {"local_ms_per_rank": [round(float(v), 3) for v in allr[:, 0].tolist()],
+                 "k2_ms_per_rank": [round(float(v), 3) for v in allr[:, 1].tolist()],
+                 "exchange_ms": ex_ms, "exchange": "NCCL all-gather of per-shard (D, I) + device k-way merge"}
+
     kern_ms = sum(pre_ms) / len(pre_ms)
     flops = 2.0 * batch * (hi - lo) * D_MODEL
     achieved_tf = flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
@@ -384,6 +402,7 @@ def main():
                        "wall_ms_per_step": wall_e2e * 1e3 / args.steps},
                "gpu_launches": int(launches),
                "roofline": roofline,
+               "multi_gpu": multi,
                "cpu_baseline": cpu,
                "engine": {k: st[k] for k in ("queries", "queries_exact", "queries_uncert", "queries_overflow",
                                              "rescored", "candidates", "last_path")}}

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -143,6 +144,8 @@ struct trx_index {
     uint64_t* counters = nullptr;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     trx_stats_t st{};
+    std::mutex mu;          // one call at a time per index: the workspaces are shared (FAISS indexes are
+                            // searchable from several threads; here concurrent callers simply take turns)
 };
 
 static void free_batch_ws(BatchWs& w) {
@@ -623,6 +626,7 @@ void trx_destroy(trx_index* ix) {
 
 int trx_reset(trx_index* ix) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     TRX_CUDA(cudaDeviceSynchronize());
     free_store(ix);
@@ -643,6 +647,7 @@ int trx_reserve(trx_index* ix, int64_t n) {
 int trx_add(trx_index* ix, const float* x, int64_t n) {
     if (!ix || n < 0 || (n > 0 && !x)) { set_error("bad argument"); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     TRX_TRY(grow(ix, ix->ntotal + n));
     cudaStream_t st = ix->own_stream;
@@ -664,6 +669,7 @@ int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
     const int es = dtype_size(dtype);
     if (es == 0) { set_error("add_typed: unknown dtype %d", dtype); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     TRX_TRY(grow(ix, ix->ntotal + n));
     cudaStream_t st = ix->own_stream;
@@ -757,6 +763,7 @@ int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t*
     if (!xq || !D || !I) { set_error("null buffer"); return TRX_EINVAL; }
     if (k > 2048) { set_error("k=%d exceeds the supported maximum 2048", k); return TRX_EINVAL; }
     if (excl && !ix->has_groups) { set_error("exclude given but no groups set (trx_set_groups)"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     const bool xq_dev = is_device_ptr(xq), out_dev = is_device_ptr(D), excl_dev = is_device_ptr(excl);
     if (out_dev != is_device_ptr(I)) { set_error("D and I must both be host or both be device pointers"); return TRX_EINVAL; }

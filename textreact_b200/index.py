@@ -28,7 +28,11 @@ from ._lib import PATH_AUTO, PATH_EXACT, PATH_STREAM, PATH_UMMA  # noqa: F401
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 
+import os
+
 try:  # torch is plumbing only (device tensors, streams); numpy callers never need it
+    if os.environ.get("TRX_NO_TORCH"):      # e.g. under compute-sanitizer: keep the process small
+        raise ImportError("TRX_NO_TORCH set")
     import torch
 except Exception:  # pragma: no cover
     torch = None

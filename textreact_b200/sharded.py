@@ -76,15 +76,22 @@ class ShardedIndexFlat:
         D, I = self.local.search(xq, k, exclude=exclude, **kw)
         if not isinstance(D, torch.Tensor):
             D, I = torch.from_numpy(D), torch.from_numpy(I)
-        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-        # list-of-views form: accepted by NCCL (coalesced into one all-gather) and by gloo (CPU tests)
-        dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
-        dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
-        Dm, Im = self._merge(Dg, Ig, self.metric_type)
+        Dm, Im = self.exchange(D, I)
         if as_numpy and isinstance(Dm, torch.Tensor):
             return Dm.cpu().numpy(), Im.cpu().numpy()
         return Dm, Im
+
+    def exchange(self, D, I):
+        """The one exchange step: all-gather the per-shard [nq, k] lists, k-way merge (K5) on every rank."""
+        Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+        Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+        if D.is_cuda:     # NCCL: one ncclAllGather each, straight into the [G, nq, k] buffers
+            dist.all_gather_into_tensor(Dg, D.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(Ig, I.contiguous(), group=self.group)
+        else:             # gloo (CPU tests of the host logic): list-of-views form
+            dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
+            dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
+        return self._merge(Dg, Ig, self.metric_type)
 
     def close(self):
         if hasattr(self.local, "close"):
