@@ -389,3 +389,34 @@ def test_typed_add_equals_host_side_float32_coercion(dtype):
     Do, Io = oracle.search_seq(xb, xq, 10, L2)
     np.testing.assert_array_equal(res[0][1], Io)
     np.testing.assert_allclose(res[0][0], Do, rtol=1e-5, atol=1e-5)
+
+
+def test_certificate_bound_holds_for_every_pair():
+    """The exactness certificate rests on |bf16-pipeline score - exact score| <= |q^||x^-x| + |x||q^-q| (+ fp32
+    accumulation slack).  Check the inequality on every (query, row) pair of a sample, with the measured
+    maxima the engine uses, against float64 scores -- and that adversarial inputs (all mantissas at the
+    rounding midpoint, same sign) come close to it without crossing it."""
+    import torch
+    trx = _engine()
+    n, d, nq = 20000, 768, 130
+    rng = np.random.default_rng(191)
+    xb, xq = util.gaussian(n, d, 192), util.gaussian(nq, d, 193)
+    # adversarial block: values just below a bf16 rounding midpoint, all positive -> errors add up coherently
+    adv = (1.0 + (2.0 ** -8) * 0.999) * np.exp2(rng.integers(-2, 3, (512, d))).astype(np.float32)
+    xb[:512] = adv
+    xq[:8] = (1.0 + (2.0 ** -8) * 0.999) * np.exp2(rng.integers(-2, 3, (8, d))).astype(np.float32)
+    idx = trx.IndexFlatIP(d)
+    idx.add(xb)
+    got = idx.debug_scores_umma(torch.from_numpy(xq).cuda(), 0, n).cpu().numpy().astype(np.float64)
+    idx.close()
+    exact = xq.astype(np.float64) @ xb.astype(np.float64).T
+    xh = torch.from_numpy(xb).bfloat16().float().numpy().astype(np.float64)
+    qh = torch.from_numpy(xq).bfloat16().float().numpy().astype(np.float64)
+    ex_max = np.linalg.norm(xh - xb, axis=1).max()
+    x_max = np.linalg.norm(xb.astype(np.float64), axis=1).max()
+    bound = (np.linalg.norm(qh, axis=1) * ex_max + x_max * np.linalg.norm(qh - xq, axis=1)
+             + 2 * (d + 3) * 2.0 ** -23 * np.linalg.norm(xq.astype(np.float64), axis=1) * x_max)
+    err = np.abs(got - exact)
+    assert (err <= bound[:, None]).all(), float((err / bound[:, None]).max())
+    # the adversarial pairs use a good part of the bound: the bound is not vacuous
+    assert (err[:8, :512] / bound[:8, None]).max() > 0.2

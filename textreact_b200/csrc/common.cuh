@@ -70,7 +70,7 @@ struct __align__(16) HitRec {
 // ---- host launchers (each returns TRX_*) ---------------------------------------------------
 
 // K1: fp32 rows -> bf16 rows (pitch Kp, zero padded; L2: |x|^2 split in 3 bf16 at cols d..d+2),
-// squared norms, running max of the squared norm (as float bits).
+// squared norms; norm2_max_bits[0] = running max of |x|^2, [1] = running max of |x - bf16(x)|^2 (float bits).
 int launch_ingest(const float* x, int64_t n, int d, int Kp, int metric, __nv_bfloat16* x16,
                   float* xnorm2, uint32_t* norm2_max_bits, cudaStream_t st);
 // Raw typed array (TRX_DTYPE_*) -> fp32, elementwise, on the device (same values as numpy's astype(float32)).

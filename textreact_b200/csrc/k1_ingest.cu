@@ -28,15 +28,15 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16&
 __global__ void __launch_bounds__(256) k1_ingest_kernel(const float* __restrict__ x, int64_t n, int d, int Kp,
                                                         int metric, __nv_bfloat16* __restrict__ x16,
                                                         float* __restrict__ xnorm2,
-                                                        uint32_t* __restrict__ norm2_max_bits) {
+                                                        uint32_t* __restrict__ norm2_max_bits /*[2]: max |x|^2, max |x - bf16(x)|^2*/) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float wmax = 0.f;
+    float wmax = 0.f, emax = 0.f;
     for (int64_t r = warp0; r < n; r += nwarps) {
         const float* xr = x + r * (int64_t)d;
         __nv_bfloat16* yr = x16 + r * (int64_t)Kp;
-        float acc = 0.f;
+        float acc = 0.f, err = 0.f;   // |x|^2 and |x - bf16(x)|^2 (each difference is exact in fp32)
         if ((d & 3) == 0) {
             const float4* x4 = reinterpret_cast<const float4*>(xr);
             for (int c = lane; c < (d >> 2); c += 32) {
@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(256) k1_ingest_kernel(const float* __restrict_
                 acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
                 __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
                 __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+                const float2 lf = __bfloat1622float2(lo), hf = __bfloat1622float2(hi);
+                const float e0 = v.x - lf.x, e1 = v.y - lf.y, e2 = v.z - hf.x, e3 = v.w - hf.y;
+                err = fmaf(e0, e0, err); err = fmaf(e1, e1, err); err = fmaf(e2, e2, err); err = fmaf(e3, e3, err);
                 uint2 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&lo);
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -54,10 +57,14 @@ __global__ void __launch_bounds__(256) k1_ingest_kernel(const float* __restrict_
             for (int c = lane; c < d; c += 32) {
                 float v = __ldg(xr + c);
                 acc = fmaf(v, v, acc);
-                yr[c] = __float2bfloat16_rn(v);
+                const __nv_bfloat16 b = __float2bfloat16_rn(v);
+                const float e = v - __bfloat162float(b);
+                err = fmaf(e, e, err);
+                yr[c] = b;
             }
         }
         acc = warp_sum(acc);
+        err = warp_sum(err);
         // padding columns (and the norm split for L2)
         for (int c = d + lane; c < Kp; c += 32) yr[c] = __float2bfloat16_rn(0.f);
         __syncwarp();
@@ -69,9 +76,11 @@ __global__ void __launch_bounds__(256) k1_ingest_kernel(const float* __restrict_
                 yr[d] = a; yr[d + 1] = b; yr[d + 2] = c3;
             }
             wmax = fmaxf(wmax, acc);
+            emax = fmaxf(emax, err);
         }
     }
     if (lane == 0 && wmax > 0.f) atomicMax(norm2_max_bits, __float_as_uint(wmax));  // >= 0: bit order == value order
+    if (lane == 0 && emax > 0.f) atomicMax(norm2_max_bits + 1, __float_as_uint(emax));
 }
 
 // Typed ingestion: the reference hands FAISS int8 Morgan bits and int64 difference counts
@@ -165,17 +174,24 @@ int launch_sample_gather(const __nv_bfloat16* x16, int64_t n, int Kp, int rate, 
     return TRX_OK;
 }
 
-// Certificate slack (see DESIGN.md "exactness certificate").
-//   bf16 rounding: |q^.x^ - q.x| <= (2u + u^2) sum|q_i x_i| <= (2u+u^2) |q||x|, u = 2^-9
-//   fp32 accumulation (tensor core, prefilter) and fp32 rescore: each <= d * 2^-23 |q||x| (loose)
-//   IP : eps = (2^-8 * 1.002 + 2 d 2^-23) |q| max|x|
+// Certificate slack (see DESIGN.md "exactness certificate"): a rigorous bound on |prefilter score - fp32 score|.
+//   rounding of the operands to bf16 (q^ = bf16(q), x^ = bf16(x)):
+//       q^.x^ - q.x = q^.(x^ - x) + x.(q^ - q)   =>   |.| <= |q^| |x^ - x| + |x| |q^ - q|       (Cauchy-Schwarz)
+//     |x^ - x| is MEASURED per row at ingest (its maximum over the corpus is kept next to max |x|), |q^ - q| and
+//     |q^| per query here: no worst-case rounding model (which would give (2u + u^2)|q||x| with u = 2^-8, the bf16
+//     unit roundoff) -- typically 3x tighter, and exactly 0 for integer-valued fingerprints.
+//   fp32 accumulation (tensor core prefilter) and fp32 rescore: each <= d * 2^-23 |q||x| (loose)
+//   IP : eps = |q^| max|x^-x| + max|x| |q^-q| + 2 d 2^-23 |q| max|x|
 //   L2 : prefilter score is 2 q.x - |x|^2  ->  2x the IP slack, + 2^-22 max|x|^2 for the 3-way norm
 //        split and + 2^-21 (|q|^2 + max|x|^2) for the fp32 evaluation of |q|^2 - sum (q-x)^2.
-__device__ __forceinline__ void certificate_slack(float qn2, float xm2, int d, int metric, float& eps, float& eps_acc) {
+__device__ __forceinline__ void certificate_slack(float qn2, float qhat2, float qerr2, float xm2, float xerr2m, int d,
+                                                  int metric, float& eps, float& eps_acc) {
     float qn = sqrtf(qn2) * 1.000001f, xn = sqrtf(xm2) * 1.000001f;
     float cacc = 2.f * (float)(d + 3) * 1.1920929e-7f;
-    float c = 0.00390625f * 1.002f + cacc;
-    float e = c * qn * xn, ea = cacc * qn * xn;
+    // the squared error norms are themselves fp32 sums of d terms: inflate by (1 + d 2^-23) and a fixed 0.1 %
+    float infl = 1.001f + (float)d * 1.1920929e-7f;
+    float rnd = (sqrtf(qhat2) * sqrtf(xerr2m) + xn * sqrtf(qerr2)) * infl;
+    float e = rnd + cacc * qn * xn, ea = cacc * qn * xn;
     if (metric == TRX_METRIC_L2) {
         float extra = 2.4e-7f * xm2 + 4.8e-7f * (qn2 + xm2);
         e = 2.f * e + extra;
@@ -202,20 +218,26 @@ __global__ void __launch_bounds__(256) k1_query_prep_kernel(const float* __restr
     for (int64_t r = warp0; r < B; r += nwarps) {
         const float* qr = q + r * (int64_t)d;
         __nv_bfloat16* yr = q16 + r * (int64_t)Kp;
-        float acc = 0.f;
+        float acc = 0.f, hat = 0.f, err = 0.f;   // |q|^2, |bf16(q)|^2, |q - bf16(q)|^2
         for (int c = lane; c < d; c += 32) {
             float v = __ldg(qr + c);
             acc = fmaf(v, v, acc);
-            yr[c] = __float2bfloat16_rn(scale * __bfloat162float(__float2bfloat16_rn(v)));
+            const float vb = __bfloat162float(__float2bfloat16_rn(v));
+            hat = fmaf(vb, vb, hat);
+            err = fmaf(v - vb, v - vb, err);
+            yr[c] = __float2bfloat16_rn(scale * vb);
         }
         for (int c = d + lane; c < Kp; c += 32)
             yr[c] = __float2bfloat16_rn((metric == TRX_METRIC_L2 && c < d + 3) ? -1.f : 0.f);
         acc = warp_sum(acc);
+        hat = warp_sum(hat);
+        err = warp_sum(err);
         if (lane == 0) {
             qnorm2[r] = acc;
             if (eps != nullptr) {
                 float e, ea;
-                certificate_slack(acc, __uint_as_float(*norm2_max_bits), d, metric, e, ea);
+                certificate_slack(acc, hat, err, __uint_as_float(norm2_max_bits[0]), __uint_as_float(norm2_max_bits[1]),
+                                  d, metric, e, ea);
                 eps[r] = e; eps_acc[r] = ea;
             }
             if (cand_cnt != nullptr) cand_cnt[r] = 0u;

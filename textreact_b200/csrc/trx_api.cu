@@ -120,7 +120,7 @@ struct trx_index {
     bool has_attr = false;
     int32_t attr_below = INT32_MAX;  // rows with attr >= attr_below are ineligible (INT32_MAX: no filter)
     std::vector<int32_t> attr_sorted; // host copy, sorted: eligible fraction of a bound in O(log N)
-    uint32_t* norm2_max = nullptr;   // 1 (float bits)
+    uint32_t* norm2_max = nullptr;   // [2] float bits: max |x|^2, max |x - bf16(x)|^2 over the stored rows
     // 1/rate row sample for threshold estimation
     __nv_bfloat16* xs16 = nullptr; int64_t ns = 0, ns_cap = 0; bool sample_dirty = true;
     // options
@@ -598,9 +598,9 @@ int trx_create(int d, int metric, int device, trx_index** out) {
     DeviceGuard g(device);
     int rc = TRX_OK;
     do {
-        if ((rc = dmalloc(&ix->norm2_max, 1)) != TRX_OK) break;
+        if ((rc = dmalloc(&ix->norm2_max, 2)) != TRX_OK) break;
         if ((rc = dmalloc(&ix->counters, 4)) != TRX_OK) break;
-        if (cudaMemset(ix->norm2_max, 0, 4) != cudaSuccess || cudaMemset(ix->counters, 0, 32) != cudaSuccess ||
+        if (cudaMemset(ix->norm2_max, 0, 8) != cudaSuccess || cudaMemset(ix->counters, 0, 32) != cudaSuccess ||
             cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
             set_error("device init failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -630,7 +630,7 @@ int trx_reset(trx_index* ix) {
     DeviceGuard g(ix->device);
     TRX_CUDA(cudaDeviceSynchronize());
     free_store(ix);
-    TRX_CUDA(cudaMemset(ix->norm2_max, 0, 4));
+    TRX_CUDA(cudaMemset(ix->norm2_max, 0, 8));
     return TRX_OK;
 }
 
