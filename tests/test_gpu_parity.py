@@ -420,3 +420,29 @@ def test_certificate_bound_holds_for_every_pair():
     assert (err <= bound[:, None]).all(), float((err / bound[:, None]).max())
     # the adversarial pairs use a good part of the bound: the bound is not vacuous
     assert (err[:8, :512] / bound[:8, None]).max() > 0.2
+
+
+def test_degenerate_queries_do_not_break_the_batch():
+    """A zero query (every score ties at 0) and a NaN query in the same batch as ordinary ones: the ordinary
+    queries keep their exact answers, the zero query returns the k lowest ids, nothing hangs or crashes."""
+    trx = _engine()
+    n, d, nq, k = 30000, 128, 140, 10
+    xb, xq = util.gaussian(n, d, 201), util.gaussian(nq, d, 202)
+    xq[5] = 0.0
+    xq[9, 3] = np.nan
+    for path in (trx.PATH_UMMA, trx.PATH_EXACT):
+        D, I, st = _run(xb, xq, k, IP, path)
+        good = np.array([i for i in range(nq) if i not in (5, 9)])
+        oracle.check_parity(D[good], I[good], xb, xq[good], k, IP)
+        assert (I[5] == np.arange(k)).all() and (D[5] == 0).all()
+
+
+def test_wide_rows():
+    """d = 4096 (wider than any fingerprint the reference builds): every path still works."""
+    trx = _engine()
+    n, d, k = 12000, 4096, 10
+    xb, xq = util.gaussian(n, d, 211), util.gaussian(40, d, 212)
+    for path, nq in ((trx.PATH_UMMA, 40), (trx.PATH_STREAM, 5), (trx.PATH_EXACT, 6)):
+        D, I, st = _run(xb, xq[:nq], k, L2, path)
+        oracle.check_parity(D, I, xb, xq[:nq], k, L2)
+        assert st["last_path"] == path

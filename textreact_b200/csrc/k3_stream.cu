@@ -256,6 +256,7 @@ int launch_stream(const StreamArgs& a, int sm_count, cudaStream_t st) {
     for (int64_t q0 = 0; q0 < a.nq;) {
         int64_t left = a.nq - q0;
         int qb = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+        while (qb > 1 && (size_t)qb * a.d * sizeof(float) > 200 * 1024) qb >>= 1;   // very wide rows: fewer queries per pass
         size_t smem = (size_t)qb * a.d * sizeof(float);
         if (smem > 200 * 1024) { set_error("k3: d=%d too large for the shared-memory query tile", a.d); return TRX_EINVAL; }
         int rc;
