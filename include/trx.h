@@ -132,7 +132,10 @@ int trx_set_id_offset(trx_index* idx, int64_t offset);
 /* Tunables: "path" (TRX_PATH_*), "max_batch", "target_candidates", "sample_rate",
  * "stream_max_batch" (crossover at or below which AUTO uses the streaming kernel),
  * "umma_pair" / "pair_min_batch" (CTA-pair tiling from this batch size on),
- * "pipeline" (0: serial batches), "attr_below" (see trx_set_row_attr; 2147483647 = off), "timing". */
+ * "pipeline" (0: serial batches), "attr_below" (see trx_set_row_attr; 2147483647 = off),
+ * "dedup_groups" (1: distinct-groups mode -- of the rows that share a group (trx_set_groups) only the best
+ * one is returned, so the k results are k different texts: the consumer's deduplicate_neighbors,
+ * textreact/dataset.py:46-56 and :77, applied before truncation instead of after), "timing". */
 int trx_set_option(trx_index* idx, const char* key, double value);
 int trx_get_option(const trx_index* idx, const char* key, double* value);
 

@@ -446,3 +446,54 @@ def test_wide_rows():
         D, I, st = _run(xb, xq[:nq], k, L2, path)
         oracle.check_parity(D, I, xb, xq[:nq], k, L2)
         assert st["last_path"] == path
+
+
+def _dedup_post_filter(I, D, groups, k):
+    """textreact/dataset.py:46-56 deduplicate_neighbors (keep the first row of every text group), then head k."""
+    outI = np.full((I.shape[0], k), -1, np.int64)
+    outD = np.zeros((I.shape[0], k), np.float32)
+    for i in range(I.shape[0]):
+        seen, j = set(), 0
+        for idn, dn in zip(I[i], D[i]):
+            if idn < 0 or groups[idn] in seen:
+                continue
+            seen.add(groups[idn])
+            outI[i, j], outD[i, j] = idn, dn
+            j += 1
+            if j == k:
+                break
+        assert j == k
+    return outD, outI
+
+
+@pytest.mark.parametrize("path_name", ["umma", "stream", "exact", "starved"])
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_distinct_groups_mode_equals_dedup_post_filter(path_name, metric):
+    """dedup=True returns k rows of k different groups: identical to searching deeper (k x largest group) and
+    running the consumer's deduplicate_neighbors -- with the gold-removed mask on top."""
+    trx = _engine()
+    n, d, k, gsz = 40000, 128, 20, 4
+    nq = 5 if path_name == "stream" else 150
+    # near-duplicate rows inside a group (same paragraph, slightly different reaction): they crowd the top
+    base = util.clustered_unit(n // gsz, d, 221)
+    xb = (np.repeat(base, gsz, axis=0) + 0.02 * util.gaussian(n, d, 222)).astype(np.float32)
+    groups = (np.arange(n) // gsz).astype(np.int32)
+    xq = util.clustered_unit(nq, d, 223)
+    excl = groups[np.random.default_rng(224).integers(0, n, nq)].astype(np.int32)
+    idx = trx.IndexFlat(d, metric)
+    idx.add(xb)
+    idx.set_groups(groups)
+    path = {"umma": trx.PATH_UMMA, "stream": trx.PATH_STREAM, "exact": trx.PATH_EXACT, "starved": trx.PATH_UMMA}[path_name]
+    idx.set_option("path", path)
+    if path_name == "starved":
+        idx.set_option("target_candidates", 32)         # too few candidates: the fallbacks must dedup as well
+    D, I = idx.search(xq, k, exclude=excl, dedup=True)
+    Dd, Id = idx.search(xq, k * gsz, exclude=excl)       # deeper, not deduplicated (dedup is per call: off again)
+    Dr, Ir = _dedup_post_filter(Id, Dd, groups, k)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
+    g = groups[I]
+    assert all(len(set(row.tolist())) == k for row in g) and not (g == excl[:, None]).any()
+    if path_name == "starved":
+        assert idx.stats()["queries_exact"] > 0
+    idx.close()

@@ -121,6 +121,7 @@ struct RescoreArgs {
     const float* q32; int64_t nq;
     const int32_t* groups; const int32_t* excl;
     const int32_t* attr; int32_t attr_below;   // nullable: rows with attr[row] >= attr_below are ineligible
+    int dedup;                                 // 1: distinct-groups mode -- only the best row of a group is returned
     int k; int metric; int64_t id_offset;
     float* D; int64_t* I;
     int32_t* fb_list; uint32_t* fb_count;  // queries that need the exact scan
@@ -149,6 +150,10 @@ int umma_init();  // resolves cuTensorMapEncodeTiled
 int umma_num_slices(int64_t n, int64_t nq, int sm_count, bool pair);  // S of the SLOTMAX mode (out = slots[nq][S][32])
 // r-th largest of the S*32 slot maxima of each query -> thr (any S; S <= 8 stays in one warp's registers)
 int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st);
+
+// Exact path, distinct-groups mode: Dx/Ix [nq, kx] sorted results (global ids) -> first k group leaders per row.
+int launch_dedup_rows(const float* Dx, const int64_t* Ix, int kx, const int32_t* groups, int64_t id_offset, int k,
+                      bool l2, const int32_t* qmap, int64_t nq, float* D, int64_t* I, cudaStream_t st);
 
 // K5: merge G sorted lists per query.
 int launch_merge(int metric, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, float* D,

@@ -6,6 +6,7 @@
 // ("larger is better": IP score, or minus squared distance for L2), ties by ascending id --
 // the (val, id) comparison of FAISS heaps.
 #include <float.h>
+#include <limits.h>
 
 #include "common.cuh"
 
@@ -279,12 +280,17 @@ __device__ __forceinline__ float exact_score_warp(const float* __restrict__ xr, 
 template <int METRIC>
 __global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: keys[cap] u64 | ekeys[cap] u64 | q[d] f32
+    // layout: keys[cap] u64 | ekeys[cap] u64 | q[dpad] f32 | dedup only: sgrp[cap] i32 | oidx[k] i32 | slead[cap] u8
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* ekeys = keys + a.cap;
     float* sq = reinterpret_cast<float*>(ekeys + a.cap);
+    int32_t* sgrp = reinterpret_cast<int32_t*>(sq + ((a.d + 3) & ~3));
+    int32_t* oidx = sgrp + a.cap;
+    uint8_t* slead = reinterpret_cast<uint8_t*>(oidx + a.k);
     __shared__ uint32_t s_valid;
     __shared__ float s_qn2;
+    __shared__ int s_cnt[1024];
+    __shared__ int s_kpos, s_nlead;
 
     const int64_t q = blockIdx.x;
     const int64_t oq = a.qmap ? (int64_t)a.qmap[q] : q;   // caller-visible query index
@@ -341,6 +347,7 @@ __global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
     const bool complete = !(thr > -INFINITY);  // every eligible row is in the list
 
     int m_done = 0;
+    int s_have = 0, s_pos = 0;       // results available / position of the k-th one after the last round
     int m = (2 * k + 56 + 7) & ~7;   // first round sized so the certificate usually holds at once
     if (m > n_valid || complete) m = n_valid;
     bool certified = false;
@@ -353,13 +360,51 @@ __global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
         const int P2 = next_pow2(m);
         for (int i = m + threadIdx.x; i < P2; i += blockDim.x) ekeys[i] = KEY_SENTINEL;
         bitonic_sort_u64(ekeys, P2);  // includes the leading barrier
+        // distinct-groups mode: only the best row of each group counts ("leaders", in exact-score order)
+        int n_have = m, kpos = k - 1;
+        if (a.dedup) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) sgrp[i] = __ldg(a.groups + key_id(ekeys[i]));
+            __syncthreads();
+            const int C = (m + (int)blockDim.x - 1) / (int)blockDim.x;
+            const int lo = min(m, (int)threadIdx.x * C), hi = min(m, lo + C);
+            int cnt = 0;
+            for (int i = lo; i < hi; i++) {
+                const int g = sgrp[i];
+                bool lead = true;
+                for (int j = 0; j < i; j++)
+                    if (sgrp[j] == g) { lead = false; break; }
+                slead[i] = lead ? 1 : 0;
+                cnt += lead ? 1 : 0;
+            }
+            s_cnt[threadIdx.x] = cnt;
+            if (threadIdx.x == 0) s_kpos = -1;
+            __syncthreads();
+            for (int off = 1; off < (int)blockDim.x; off <<= 1) {   // inclusive scan of the per-thread leader counts
+                int v = threadIdx.x >= (unsigned)off ? s_cnt[threadIdx.x - off] : 0;
+                __syncthreads();
+                s_cnt[threadIdx.x] += v;
+                __syncthreads();
+            }
+            int pos = s_cnt[threadIdx.x] - cnt;     // leaders before this thread's chunk
+            for (int i = lo; i < hi; i++) {
+                if (slead[i]) {
+                    if (pos < k) oidx[pos] = i;
+                    if (pos == k - 1) s_kpos = i;
+                    pos++;
+                }
+            }
+            if (threadIdx.x == blockDim.x - 1) s_nlead = s_cnt[threadIdx.x];
+            __syncthreads();
+            n_have = s_nlead; kpos = s_kpos;
+        }
         if (m == n_valid && complete) certified = true;
-        else if (m >= k) {
-            float sk = key_score(ekeys[k - 1]);
+        else if (n_have >= k) {
+            float sk = key_score(ekeys[kpos]);
             if (METRIC == TRX_METRIC_L2) sk += qn2;  // prefilter domain: |q|^2 - dist
             float bound = m < n_valid ? key_score(keys[m]) : thr;
             certified = sk > bound + eps;
         }
+        s_have = n_have; s_pos = kpos;   // (thread-uniform values kept for the epilogue)
         if (certified || m == n_valid) break;
         m_done = m;
         m = 2 * m < n_valid ? 2 * m : n_valid;
@@ -374,14 +419,14 @@ __global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
             uint32_t slot = atomicAdd(a.fb_count, 1u);
             a.fb_list[slot] = (int32_t)oq;
             // every true top-k row scores at least the k-th best exact score seen so far
-            a.fb_thr[slot] = m >= k ? key_score(ekeys[k - 1]) - a.eps_acc[q] : -INFINITY;
+            a.fb_thr[slot] = s_have >= k ? key_score(ekeys[s_pos]) - a.eps_acc[q] : -INFINITY;
             atomicAdd((unsigned long long*)&a.counters[1], 1ull);
         }
         return;
     }
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        if (j < m) {
-            uint64_t key = ekeys[j];
+        if (j < s_have) {
+            uint64_t key = ekeys[a.dedup ? oidx[j] : j];
             float sc = key_score(key);
             Dq[j] = METRIC == TRX_METRIC_L2 ? -sc : sc;
             Iq[j] = (int64_t)key_id(key) + a.id_offset;
@@ -391,7 +436,11 @@ __global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
 
 int launch_rescore(const RescoreArgs& a, cudaStream_t st) {
     if (a.nq <= 0) return TRX_OK;
-    size_t smem = (size_t)a.cap * 16 + (size_t)a.d * 4;
+    size_t smem = (size_t)a.cap * 16 + (size_t)((a.d + 3) & ~3) * 4;
+    if (a.dedup) {
+        if (a.groups == nullptr) { set_error("k4: distinct-groups mode needs groups"); return TRX_EINVAL; }
+        smem += (size_t)a.cap * 4 + (size_t)a.k * 4 + (size_t)a.cap;
+    }
     if (smem > 200 * 1024) { set_error("k4: cap=%d d=%d exceed shared memory", a.cap, a.d); return TRX_EINVAL; }
     const int threads = a.nq <= 296 ? 1024 : 256;
     if (a.metric == TRX_METRIC_L2) {
@@ -403,6 +452,58 @@ int launch_rescore(const RescoreArgs& a, cudaStream_t st) {
         TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)a.nq, threads, smem, st>>>(a);
     }
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// distinct-groups filter for the exact path: rows of kx sorted results -> the first k group leaders
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) dedup_rows_kernel(const float* __restrict__ Dx, const int64_t* __restrict__ Ix,
+                                                         int kx, const int32_t* __restrict__ groups, int64_t id_offset,
+                                                         int k, float fill, const int32_t* __restrict__ qmap,
+                                                         float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ int32_t sg[];   // [kx] group of each result (INT32_MIN for padding)
+    __shared__ int s_out;
+    const int64_t q = blockIdx.x;
+    const int64_t oq = qmap ? (int64_t)qmap[q] : q;
+    const float* Dr = Dx + q * kx;
+    const int64_t* Ir = Ix + q * kx;
+    for (int i = threadIdx.x; i < kx; i += blockDim.x) {
+        const int64_t id = Ir[i];
+        sg[i] = id >= 0 ? __ldg(groups + (id - id_offset)) : INT32_MIN;
+    }
+    if (threadIdx.x == 0) s_out = 0;
+    __syncthreads();
+    // leaders are taken in order by one warp: ballot over 32 results at a time keeps the order stable
+    if (threadIdx.x < 32) {
+        int out = 0;
+        for (int i0 = 0; i0 < kx && out < k; i0 += 32) {
+            const int i = i0 + threadIdx.x;
+            bool lead = false;
+            if (i < kx && Ir[i] >= 0) {
+                lead = true;
+                const int g = sg[i];
+                for (int j = 0; j < i; j++)
+                    if (sg[j] == g && Ir[j] >= 0) { lead = false; break; }
+            }
+            const uint32_t b = __ballot_sync(0xffffffffu, lead);
+            const int pos = out + __popc(b & ((1u << threadIdx.x) - 1u));
+            if (lead && pos < k) { D[oq * k + pos] = Dr[i]; I[oq * k + pos] = Ir[i]; }
+            out += __popc(b);
+        }
+        if (threadIdx.x == 0) s_out = out < k ? out : k;
+    }
+    __syncthreads();
+    for (int j = s_out + threadIdx.x; j < k; j += blockDim.x) { D[oq * k + j] = fill; I[oq * k + j] = -1; }
+}
+
+int launch_dedup_rows(const float* Dx, const int64_t* Ix, int kx, const int32_t* groups, int64_t id_offset, int k,
+                      bool l2, const int32_t* qmap, int64_t nq, float* D, int64_t* I, cudaStream_t st) {
+    if (nq <= 0) return TRX_OK;
+    dedup_rows_kernel<<<(unsigned)nq, 128, (size_t)kx * 4, st>>>(Dx, Ix, kx, groups, id_offset, k, l2 ? FLT_MAX : -FLT_MAX,
+                                                                qmap, D, I);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;

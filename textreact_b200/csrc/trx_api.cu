@@ -120,6 +120,9 @@ struct trx_index {
     bool has_attr = false;
     int32_t attr_below = INT32_MAX;  // rows with attr >= attr_below are ineligible (INT32_MAX: no filter)
     std::vector<int32_t> attr_sorted; // host copy, sorted: eligible fraction of a bound in O(log N)
+    int dedup = 0;                   // distinct-groups mode: only the best row of a group is returned
+    int group_max = 0; double group_avg = 1.0;   // largest / mean group size (computed on first use)
+    float* xD = nullptr; int64_t* xI = nullptr; size_t x_elems = 0;   // exact path + dedup: widened result rows
     uint32_t* norm2_max = nullptr;   // [2] float bits: max |x|^2, max |x - bf16(x)|^2 over the stored rows
     // 1/rate row sample for threshold estimation
     __nv_bfloat16* xs16 = nullptr; int64_t ns = 0, ns_cap = 0; bool sample_dirty = true;
@@ -164,6 +167,7 @@ static void free_batch_ws(BatchWs& w) {
 static void free_ws(trx_index* ix) {
     free_batch_ws(ix->ws[0]); free_batch_ws(ix->ws[1]);
     dfree(ix->fb_list2); dfree(ix->thr2); dfree(ix->neg_inf); dfree(ix->qfb); dfree(ix->exfb); dfree(ix->xscores);
+    dfree(ix->xD); dfree(ix->xI); ix->x_elems = 0;
     ix->fb_batch = 0; ix->xscores_elems = 0;
 }
 
@@ -204,11 +208,31 @@ static double eligible_fraction(const trx_index* ix) {
 
 // Candidates per query the prefilter aims for.  The threshold is sized on ALL rows; with an attribute filter
 // only a fraction f of the candidates is eligible, so the target grows by 1/f (bounded by K4's list size).
+static bool dedup_active(const trx_index* ix) { return ix->dedup && ix->has_groups; }
+
 static int effective_target(const trx_index* ix, int k) {
     int T = std::max(ix->target, 4 * k);
-    const double f = eligible_fraction(ix);
-    if (f < 1.0) T = (int)std::min<double>(2048.0, std::ceil(T / std::max(f, 1e-6)));
+    double scale = 1.0 / std::max(eligible_fraction(ix), 1e-6);
+    if (dedup_active(ix)) scale *= std::max(1.0, ix->group_avg);   // k distinct groups need ~k * (group size) rows
+    if (scale > 1.0) T = (int)std::min<double>(2048.0, std::ceil(T * scale));
     return T;
+}
+
+// largest and mean group size: sizes the candidate target and the widened exact scan of the distinct-groups mode
+static int ensure_group_stats(trx_index* ix) {
+    if (!dedup_active(ix) || ix->group_max > 0) return TRX_OK;
+    std::vector<int32_t> g;
+    try { g.resize((size_t)ix->ntotal); } catch (...) { set_error("host allocation failed"); return TRX_ENOMEM; }
+    TRX_CUDA(cudaMemcpy(g.data(), ix->groups, (size_t)ix->ntotal * 4, cudaMemcpyDeviceToHost));
+    std::sort(g.begin(), g.end());
+    int64_t ngroups = 0; int best = 0, run = 0;
+    for (size_t i = 0; i < g.size(); i++) {
+        if (i == 0 || g[i] != g[i - 1]) { ngroups++; run = 0; }
+        if (++run > best) best = run;
+    }
+    ix->group_max = std::max(best, 1);
+    ix->group_avg = ngroups > 0 ? (double)g.size() / (double)ngroups : 1.0;
+    return TRX_OK;
 }
 
 static int candidate_cap(const trx_index* ix, int k) {
@@ -295,6 +319,24 @@ static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, 
         TRX_TRY(dmalloc(&ix->xscores, (size_t)rows * N));
         ix->xscores_elems = (size_t)rows * N;
     }
+    // distinct-groups mode: the top k * (largest group) rows always contain k group leaders
+    const bool dd = dedup_active(ix);
+    int kx = k;
+    if (dd) {
+        const int64_t want = (int64_t)k * ix->group_max;
+        if (want > 2048) {
+            set_error("distinct-groups search on the exact path needs k * largest group <= 2048 (k=%d, largest group=%d)",
+                      k, ix->group_max);
+            return TRX_EINVAL;
+        }
+        kx = (int)want;
+        if ((size_t)rows * kx > ix->x_elems) {
+            dfree(ix->xD); dfree(ix->xI);
+            TRX_TRY(dmalloc(&ix->xD, (size_t)rows * kx));
+            TRX_TRY(dmalloc(&ix->xI, (size_t)rows * kx));
+            ix->x_elems = (size_t)rows * kx;
+        }
+    }
     for (int64_t q0 = 0; q0 < nq; q0 += rows) {
         int64_t nb = std::min(rows, nq - q0);
         StreamArgs a{};
@@ -306,9 +348,16 @@ static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, 
         a.out = ix->xscores; a.out_ld = N;
         a.metric = ix->metric; a.bf16 = false; a.append = false;
         TRX_TRY(launch_stream(a, ix->sm_count, st));
-        TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, k, ix->metric == TRX_METRIC_L2, ix->id_offset,
-                                  qmap_dev ? qmap_dev + q0 : nullptr,
-                                  qmap_dev ? Dd : Dd + q0 * k, qmap_dev ? Id : Id + q0 * k, st));
+        const bool l2 = ix->metric == TRX_METRIC_L2;
+        if (!dd) {
+            TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, k, l2, ix->id_offset, qmap_dev ? qmap_dev + q0 : nullptr,
+                                      qmap_dev ? Dd : Dd + q0 * k, qmap_dev ? Id : Id + q0 * k, st));
+        } else {
+            TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, kx, l2, ix->id_offset, nullptr, ix->xD, ix->xI, st));
+            TRX_TRY(launch_dedup_rows(ix->xD, ix->xI, kx, ix->groups, ix->id_offset, k, l2,
+                                      qmap_dev ? qmap_dev + q0 : nullptr, nb, qmap_dev ? Dd : Dd + q0 * k,
+                                      qmap_dev ? Id : Id + q0 * k, st));
+        }
     }
     ix->st.queries_exact += nq;
     return TRX_OK;
@@ -326,6 +375,7 @@ static RescoreArgs rescore_args(const trx_index* ix, const BatchWs& w, int k) {
     ra.x32 = ix->x32; ra.d = ix->d; ra.n = ix->ntotal; ra.q32 = w.qdev; ra.nq = w.B;
     ra.groups = ix->has_groups ? ix->groups : nullptr; ra.excl = w.exdev;
     ra.attr = attr_active(ix) ? ix->attr : nullptr; ra.attr_below = ix->attr_below;
+    ra.dedup = dedup_active(ix) ? 1 : 0;
     ra.k = k; ra.metric = ix->metric; ra.id_offset = ix->id_offset;
     ra.D = w.Dd; ra.I = w.Id; ra.fb_list = w.fb_list; ra.fb_count = w.fb_count;
     ra.fb_thr = w.fb_thr; ra.eps_acc = w.eps_acc; ra.qmap = nullptr; ra.counters = ix->counters;
@@ -711,6 +761,7 @@ int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
 
 int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    ix->group_max = 0; ix->group_avg = 1.0;
     if (gsrc == nullptr) { ix->has_groups = false; return TRX_OK; }
     if (n != ix->ntotal) { set_error("set_groups: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
@@ -769,6 +820,7 @@ int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t*
     if (out_dev != is_device_ptr(I)) { set_error("D and I must both be host or both be device pointers"); return TRX_EINVAL; }
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
     ix->st.searches++;
+    TRX_TRY(ensure_group_stats(ix));
     if (ix->ntotal == 0) {  // FAISS: empty index -> all -1
         std::vector<float> dfill((size_t)nq * k, ix->metric == TRX_METRIC_L2 ? FLT_MAX : -FLT_MAX);
         std::vector<int64_t> ifill((size_t)nq * k, -1);
@@ -817,6 +869,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->timing = v != 0;
     } else if (!strcmp(key, "pipeline")) {
         ix->pipeline = v != 0;
+    } else if (!strcmp(key, "dedup_groups")) {
+        ix->dedup = v != 0;
     } else if (!strcmp(key, "attr_below")) {
         ix->attr_below = v >= 2147483647.0 ? INT32_MAX : (v <= -2147483648.0 ? INT32_MIN : (int32_t)v);
     } else if (!strcmp(key, "thr_bias")) {
@@ -842,6 +896,7 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "pair_min_batch")) *v = ix->pair_min_batch;
     else if (!strcmp(key, "pipeline")) *v = ix->pipeline;
     else if (!strcmp(key, "attr_below")) *v = ix->attr_below;
+    else if (!strcmp(key, "dedup_groups")) *v = ix->dedup;
     else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }

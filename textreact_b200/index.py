@@ -14,7 +14,8 @@ dimension raises ``AssertionError`` (FAISS behaviour); engine failures raise ``R
 / ``MemoryError``.  Extensions, all keyword-only and ignored by the reference script:
 ``exclude=`` (gold-removed mode, textreact/dataset.py:74-76 lifted into the engine),
 ``set_groups``, ``set_row_attr`` / ``attr_below=`` (the ``--before`` year restriction, :102-103),
-``search_self`` (train->train search, :114-115), torch CUDA tensors in / out, ``device=``.
+``search_self`` (train->train search, :114-115), ``dedup=True`` (distinct text groups, the consumer's
+``deduplicate_neighbors``, textreact/dataset.py:46-56), torch CUDA tensors in / out, ``device=``.
 """
 from __future__ import annotations
 
@@ -111,12 +112,13 @@ class IndexFlat:
         _lib.check(self._L.trx_add(self._h, ptr, n), "add")
         del keep
 
-    def search(self, x, k, *, D=None, I=None, exclude=None, attr_below=None, params=None):
+    def search(self, x, k, *, D=None, I=None, exclude=None, attr_below=None, dedup=False, params=None):
         assert k > 0
         ptr, nq, keep, on_dev = _as_f32_matrix(x, self.d)
-        return self._search(ptr, nq, keep, on_dev, k, D, I, exclude, attr_below, None)
+        return self._search(ptr, nq, keep, on_dev, k, D, I, exclude, attr_below, None, dedup)
 
-    def search_self(self, k, start=0, stop=None, *, D=None, I=None, exclude=None, attr_below=None, device=False):
+    def search_self(self, k, start=0, stop=None, *, D=None, I=None, exclude=None, attr_below=None, dedup=False,
+                    device=False):
         """``search(xb[start:stop], k)`` with the rows already stored in the index as the queries -- the
         reference's train->train search (retrieve/retrieve_faiss.py:114-115, ``query_fps = train_fps``)
         without sending the corpus to the GPU a second time.  numpy out unless ``device=True``."""
@@ -125,9 +127,9 @@ class IndexFlat:
         start = int(start)
         assert 0 <= start <= stop <= self.ntotal, f"rows [{start}, {stop}) outside [0, {self.ntotal})"
         keep = torch.empty(0, device=torch.device("cuda", self.device)) if device else None
-        return self._search(None, stop - start, keep, bool(device), k, D, I, exclude, attr_below, start)
+        return self._search(None, stop - start, keep, bool(device), k, D, I, exclude, attr_below, start, dedup)
 
-    def _search(self, ptr, nq, keep, on_dev, k, D, I, exclude, attr_below, self_row0):
+    def _search(self, ptr, nq, keep, on_dev, k, D, I, exclude, attr_below, self_row0, dedup=False):
         ex_ptr, ex_keep = (None, None)
         if exclude is not None:
             ex_ptr, ex_keep = _as_i32_vector(exclude, nq, "exclude")
@@ -150,6 +152,8 @@ class IndexFlat:
             out = (Dn, In)
         if attr_below is not None:
             self.set_option("attr_below", attr_below)
+        if dedup:
+            self.set_option("dedup_groups", 1)
         try:
             if self_row0 is None:
                 _lib.check(self._L.trx_search(self._h, ptr, nq, int(k), ex_ptr, dptr, iptr, stream), "search")
@@ -159,6 +163,8 @@ class IndexFlat:
         finally:
             if attr_below is not None:
                 self.set_option("attr_below", 2147483647)
+            if dedup:
+                self.set_option("dedup_groups", 0)
         del keep, ex_keep
         return out
 
