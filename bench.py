@@ -127,10 +127,13 @@ def host_threads():
 def run_reference(args):
     """--impl reference: FAISS CPU flat search (the oracle restatement; real faiss is not installable
     here: un-vendored, un-pinned, no network) on the box's host cores."""
-    import numpy as np
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is meant to use every host core
+    if os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    import numpy as np
     rows, batch, name = workload(args.gpus, args)
     sample_rows, sample_q = min(rows, 400_000), min(batch, 1024)
     rng = np.random.default_rng(1234)

@@ -498,3 +498,16 @@ def test_distinct_groups_mode_equals_dedup_post_filter(path_name, metric):
     if path_name == "starved":
         assert idx.stats()["queries_exact"] > 0
     idx.close()
+
+
+def test_modes_without_their_side_data_are_errors():
+    trx = _engine()
+    xb = util.gaussian(2000, 32, 231)
+    idx = trx.IndexFlatIP(32)
+    idx.add(xb)
+    for kw in ({"dedup": True}, {"attr_below": 5}, {"exclude": np.zeros(3, np.int32)}):
+        with pytest.raises(RuntimeError, match="trx_set_groups|trx_set_row_attr"):
+            idx.search(xb[:3], 4, **kw)
+    D, I = idx.search(xb[:3], 4)                 # the failed calls left no option behind
+    assert (I[:, 0] == np.arange(3)).all()
+    idx.close()

@@ -814,6 +814,8 @@ int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t*
     if (!xq || !D || !I) { set_error("null buffer"); return TRX_EINVAL; }
     if (k > 2048) { set_error("k=%d exceeds the supported maximum 2048", k); return TRX_EINVAL; }
     if (excl && !ix->has_groups) { set_error("exclude given but no groups set (trx_set_groups)"); return TRX_EINVAL; }
+    if (ix->dedup && !ix->has_groups) { set_error("dedup_groups set but no groups set (trx_set_groups)"); return TRX_EINVAL; }
+    if (ix->attr_below != INT32_MAX && !ix->has_attr) { set_error("attr_below set but no row attributes (trx_set_row_attr)"); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     const bool xq_dev = is_device_ptr(xq), out_dev = is_device_ptr(D), excl_dev = is_device_ptr(excl);
