@@ -277,8 +277,50 @@ __device__ __forceinline__ float exact_score_warp(const float* __restrict__ xr, 
     return METRIC == TRX_METRIC_INNER_PRODUCT ? acc : -acc;
 }
 
+// Two rows at once: twice the gather bytes in flight per warp (the rescore is bound by the latency of ~3 KB row
+// gathers); every row keeps exactly the summation order of exact_score_warp, so scores do not depend on the pairing.
 template <int METRIC>
-__global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
+__device__ __forceinline__ void exact_score_warp2(const float* __restrict__ xa, const float* __restrict__ xb,
+                                                  const float* __restrict__ sq, int d, int lane, float& ea, float& eb) {
+    float acc0 = 0.f, acc1 = 0.f;
+    if ((d & 3) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(xa);
+        const float4* b4 = reinterpret_cast<const float4*>(xb);
+        const float4* q4 = reinterpret_cast<const float4*>(sq);
+#pragma unroll 2
+        for (int c = lane; c < (d >> 2); c += 32) {
+            const float4 x = __ldg(a4 + c);
+            const float4 y = __ldg(b4 + c);
+            const float4 q = q4[c];
+            if (METRIC == TRX_METRIC_INNER_PRODUCT) {
+                acc0 = fmaf(x.x, q.x, acc0); acc0 = fmaf(x.y, q.y, acc0);
+                acc0 = fmaf(x.z, q.z, acc0); acc0 = fmaf(x.w, q.w, acc0);
+                acc1 = fmaf(y.x, q.x, acc1); acc1 = fmaf(y.y, q.y, acc1);
+                acc1 = fmaf(y.z, q.z, acc1); acc1 = fmaf(y.w, q.w, acc1);
+            } else {
+                float t0 = q.x - x.x, t1 = q.y - x.y, t2 = q.z - x.z, t3 = q.w - x.w;
+                acc0 = fmaf(t0, t0, acc0); acc0 = fmaf(t1, t1, acc0);
+                acc0 = fmaf(t2, t2, acc0); acc0 = fmaf(t3, t3, acc0);
+                float u0 = q.x - y.x, u1 = q.y - y.y, u2 = q.z - y.z, u3 = q.w - y.w;
+                acc1 = fmaf(u0, u0, acc1); acc1 = fmaf(u1, u1, acc1);
+                acc1 = fmaf(u2, u2, acc1); acc1 = fmaf(u3, u3, acc1);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        }
+        ea = METRIC == TRX_METRIC_INNER_PRODUCT ? acc0 : -acc0;
+        eb = METRIC == TRX_METRIC_INNER_PRODUCT ? acc1 : -acc1;
+    } else {
+        ea = exact_score_warp<METRIC>(xa, sq, d, lane);
+        eb = exact_score_warp<METRIC>(xb, sq, d, lane);
+    }
+}
+
+template <int METRIC, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: keys[cap] u64 | ekeys[cap] u64 | q[dpad] f32 | dedup only: sgrp[cap] i32 | oidx[k] i32 | slead[cap] u8
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
@@ -352,10 +394,15 @@ __global__ void __launch_bounds__(1024) k4_rescore_kernel(RescoreArgs a) {
     if (m > n_valid || complete) m = n_valid;
     bool certified = false;
     for (;;) {
-        for (int i = m_done + wid; i < m; i += nwarp) {
-            uint32_t row = key_id(keys[i]);
-            float e = exact_score_warp<METRIC>(a.x32 + (int64_t)row * a.d, sq, a.d, lane);
-            if (lane == 0) ekeys[i] = pack_key(e, row);
+        for (int i = m_done + 2 * wid; i < m; i += 2 * nwarp) {
+            const bool two = i + 1 < m;
+            const uint32_t row0 = key_id(keys[i]), row1 = two ? key_id(keys[i + 1]) : row0;
+            float e0, e1;
+            exact_score_warp2<METRIC>(a.x32 + (int64_t)row0 * a.d, a.x32 + (int64_t)row1 * a.d, sq, a.d, lane, e0, e1);
+            if (lane == 0) {
+                ekeys[i] = pack_key(e0, row0);
+                if (two) ekeys[i + 1] = pack_key(e1, row1);
+            }
         }
         const int P2 = next_pow2(m);
         for (int i = m + threadIdx.x; i < P2; i += blockDim.x) ekeys[i] = KEY_SENTINEL;
@@ -442,16 +489,16 @@ int launch_rescore(const RescoreArgs& a, cudaStream_t st) {
         smem += (size_t)a.cap * 4 + (size_t)a.k * 4 + (size_t)a.cap;
     }
     if (smem > 200 * 1024) { set_error("k4: cap=%d d=%d exceed shared memory", a.cap, a.d); return TRX_EINVAL; }
-    const int threads = a.nq <= 296 ? 1024 : 256;
-    if (a.metric == TRX_METRIC_L2) {
-        auto kern = k4_rescore_kernel<TRX_METRIC_L2>;
-        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)a.nq, threads, smem, st>>>(a);
-    } else {
-        auto kern = k4_rescore_kernel<TRX_METRIC_INNER_PRODUCT>;
-        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)a.nq, threads, smem, st>>>(a);
-    }
+    const bool wide = a.nq <= 296;   // few queries: 1024-thread CTAs so that one query's gathers use 32 warps
+#define TRX_K4(M, NT)                                                                                        \
+    do {                                                                                                     \
+        auto kern = k4_rescore_kernel<M, NT>;                                                                \
+        TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        kern<<<(unsigned)a.nq, NT, smem, st>>>(a);                                                           \
+    } while (0)
+    if (a.metric == TRX_METRIC_L2) { if (wide) TRX_K4(TRX_METRIC_L2, 1024); else TRX_K4(TRX_METRIC_L2, 256); }
+    else { if (wide) TRX_K4(TRX_METRIC_INNER_PRODUCT, 1024); else TRX_K4(TRX_METRIC_INNER_PRODUCT, 256); }
+#undef TRX_K4
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;
