@@ -393,9 +393,11 @@ def main():
     if rank == 0:
         out = {"metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": n_gpus, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "strong" if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "bf16 prefilter + f32 rescore",
+               "scaling": "strong" if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "bf16",
                "data": "synthetic",
                "config": {"workload": name, "rows": rows, "rows_per_gpu": hi - lo, "batch": batch, "k": K, "d": D_MODEL,
+                          "dtype_detail": "bf16 tcgen05 prefilter (fp32 accumulate) + exact fp32 rescore with certificate: "
+                                          "results are the fp32 flat-search answer",
                           "dist": "iid N(0,1) fp32, seeds 1234+rank / 4321", "l2_policy": "inputs_exceed_l2 "
                           f"(bf16 corpus shard {2 * (hi - lo) * D_MODEL / 1e9:.1f} GB >> 126 MB L2)",
                           "scored_pairs_per_s": qps * rows},
