@@ -1,0 +1,101 @@
+"""GPU: seeded random shapes / modes against the oracle -- the cases nobody thought of.
+
+Each case draws (n, d, nq, k, metric, path, data distribution, mask, attribute filter, dedup, max_batch) from a
+seeded generator, runs the engine through the C ABI and applies the north_star parity rule (or, with dedup, the
+consumer's deduplicate_neighbors on a deeper plain search)."""
+import numpy as np
+import pytest
+
+from oracle import cpu_flat as oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _draw(seed):
+    rng = np.random.default_rng(1000 + seed)
+    d = int(rng.choice([8, 31, 64, 100, 200, 384, 768, 1024]))
+    n = int(rng.choice([300, 5000, 9000, 20000, 45000]))
+    nq = int(rng.choice([1, 2, 3, 7, 33, 64, 129, 300]))
+    k = int(rng.choice([1, 5, 20, 100]))
+    metric = int(rng.integers(0, 2))
+    path = int(rng.integers(0, 4))                      # AUTO / EXACT / STREAM / UMMA
+    dist = str(rng.choice(["gauss", "unit", "bits", "scaled"]))
+    return rng, dict(d=d, n=n, nq=nq, k=k, metric=metric, path=path, dist=dist,
+                     mask=bool(rng.integers(0, 2)), attr=bool(rng.integers(0, 3) == 0), dedup=bool(rng.integers(0, 4) == 0),
+                     max_batch=int(rng.choice([64, 1000, 8192])))
+
+
+def _data(rng, c):
+    n, d, nq = c["n"], c["d"], c["nq"]
+    if c["dist"] == "gauss":
+        return util.gaussian(n, d, int(rng.integers(1 << 30))), util.gaussian(nq, d, int(rng.integers(1 << 30)))
+    if c["dist"] == "unit":
+        return util.clustered_unit(n, d, int(rng.integers(1 << 30))), util.clustered_unit(nq, d, int(rng.integers(1 << 30)))
+    if c["dist"] == "bits":
+        xb = util.fingerprints(n, d, int(rng.integers(1 << 30)), p=0.1)
+        return xb, xb[rng.integers(0, n, nq)]
+    xb = util.gaussian(n, d, int(rng.integers(1 << 30))) * np.exp(rng.normal(0, 1.0, (n, 1))).astype(np.float32)
+    return xb, util.gaussian(nq, d, int(rng.integers(1 << 30))) * 3.0
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_configuration(seed):
+    import textreact_b200 as trx
+    rng, c = _draw(seed)
+    xb, xq = _data(rng, c)
+    n, nq, k, metric = c["n"], c["nq"], c["k"], c["metric"]
+    if c["path"] == trx.PATH_STREAM and nq > 8:
+        xq = xq[:8]; nq = 8
+    gsz = int(rng.integers(1, 5))
+    groups = (rng.permutation(n) // gsz).astype(np.int32)
+    excl = groups[rng.integers(0, n, nq)].astype(np.int32) if c["mask"] else None
+    if excl is not None:
+        excl[rng.random(nq) < 0.3] = -1
+    years = rng.integers(1990, 2020, n).astype(np.int32)
+    bound = int(rng.choice([1995, 2005, 2015])) if c["attr"] else None
+    idx = trx.IndexFlat(xb.shape[1], metric)
+    half = n // 2
+    idx.add(xb[:half]); idx.add(xb[half:])
+    idx.set_groups(groups)
+    idx.set_row_attr(years)
+    idx.set_option("path", c["path"])
+    idx.set_option("max_batch", c["max_batch"])
+    kw = {}
+    if excl is not None:
+        kw["exclude"] = excl
+    if bound is not None:
+        kw["attr_below"] = bound
+    ctx = f"seed {seed}: {c} gsz {gsz}"
+    elig = np.nonzero(years < bound)[0] if bound is not None else np.arange(n)
+    if c["dedup"]:
+        deep = min(2048, k * gsz)
+        if deep > len(elig) // 2 or k * gsz > 2048:
+            idx.close()
+            pytest.skip("dedup depth not meaningful for this draw")
+        D, I = idx.search(xq, k, dedup=True, **kw)
+        Dd, Id = idx.search(xq, deep, **kw)
+        for i in range(nq):                               # consumer-side dedup of the deeper list
+            seen, want = set(), []
+            for j in Id[i]:
+                if j >= 0 and groups[j] not in seen:
+                    seen.add(groups[j]); want.append(j)
+                if len(want) == k:
+                    break
+            got = [j for j in I[i] if j >= 0]
+            if c["dist"] == "bits":                       # massive exact ties: compare scores, not ids
+                assert len(got) == len(want), ctx
+                assert len(set(groups[got].tolist())) == len(got), ctx
+            else:
+                assert got == want, ctx
+    else:
+        D, I = idx.search(xq, k, **kw)
+        sub = xb[elig]
+        gsub = groups[elig]
+        Isub = np.where(I >= 0, np.searchsorted(elig, np.maximum(I, 0)), -1)
+        assert ((I < 0) | np.isin(I, elig)).all(), ctx
+        try:
+            oracle.check_parity(D, Isub, sub, xq, k, metric, gsub if excl is not None else None, excl)
+        except AssertionError as e:
+            raise AssertionError(f"{ctx}: {e}") from None
+    idx.close()
