@@ -76,18 +76,23 @@ def test_random_configuration(seed):
         D, I = idx.search(xq, k, dedup=True, **kw)
         Dd, Id = idx.search(xq, deep, **kw)
         for i in range(nq):                               # consumer-side dedup of the deeper list
-            seen, want = set(), []
-            for j in Id[i]:
+            seen, want, wantd = set(), [], []
+            for j, dj in zip(Id[i], Dd[i]):
                 if j >= 0 and groups[j] not in seen:
-                    seen.add(groups[j]); want.append(j)
+                    seen.add(groups[j]); want.append(j); wantd.append(dj)
                 if len(want) == k:
                     break
             got = [j for j in I[i] if j >= 0]
-            if c["dist"] == "bits":                       # massive exact ties: compare scores, not ids
-                assert len(got) == len(want), ctx
-                assert len(set(groups[got].tolist())) == len(got), ctx
-            else:
-                assert got == want, ctx
+            assert len(got) == len(want), ctx
+            assert len(set(groups[got].tolist())) == len(got), ctx
+            # same scores rank by rank; ids may differ only inside a (near-)tie: the deeper search can take a
+            # different kernel path (k > 256 -> exact scan), whose fp32 summation order differs in the last bits
+            gd, wd = D[i, :len(got)].astype(np.float64), np.asarray(wantd, np.float64)
+            scale = np.maximum(np.abs(wd), 1e-30) if metric == 0 else np.maximum(np.abs(wd), 1.0)
+            assert (np.abs(gd - wd) <= 2e-5 * scale).all(), ctx
+            if c["dist"] != "bits":
+                differ = [p for p in range(len(got)) if got[p] != want[p]]
+                assert len(differ) <= 4, ctx
     else:
         D, I = idx.search(xq, k, **kw)
         sub = xb[elig]
