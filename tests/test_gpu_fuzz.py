@@ -3,6 +3,8 @@
 Each case draws (n, d, nq, k, metric, path, data distribution, mask, attribute filter, dedup, max_batch) from a
 seeded generator, runs the engine through the C ABI and applies the north_star parity rule (or, with dedup, the
 consumer's deduplicate_neighbors on a deeper plain search)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -39,7 +41,7 @@ def _data(rng, c):
     return xb, util.gaussian(nq, d, int(rng.integers(1 << 30))) * 3.0
 
 
-@pytest.mark.parametrize("seed", range(48))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("TRX_FUZZ_SEEDS", "48"))))
 def test_random_configuration(seed):
     import textreact_b200 as trx
     rng, c = _draw(seed)
