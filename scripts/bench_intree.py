@@ -25,6 +25,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import textreact_b200 as trx  # noqa: E402
+from textreact_b200 import nnfile  # noqa: E402
 from oracle import cpu_flat as oracle  # noqa: E402  (checker + cpu baseline only)
 
 
@@ -57,6 +58,20 @@ def run(name, xb, nq, k, batch, check):
     s1 = idx.stats()
     st = {key: s1[key] - s0[key] for key in ("queries", "queries_exact", "queries_uncert", "queries_overflow",
                                              "rescored", "candidates")}
+    # the same rows as queries straight from the resident copy (train->train mode), and the {id, nn} writer
+    t0 = time.perf_counter()
+    Ds, Is = idx.search_self(k, 0, nq)
+    dt_self = time.perf_counter() - t0
+    same = bool((Is == I).all() and (Ds == D).all())
+    ids = [f"US{20000000 + i // 3}_{i % 3}" for i in range(n)]
+    t0 = time.perf_counter()
+    text = nnfile.dumps_nn_json(ids[:nq], ids, I)
+    dt_write = time.perf_counter() - t0
+    sub = min(nq, 2000)
+    t0 = time.perf_counter()
+    ref = json.dumps([{'id': ids[i], 'nn': [ids[j] for j in nn]} for i, nn in enumerate(I[:sub])])   # retrieve_faiss.py:116
+    dt_ref_write = (time.perf_counter() - t0) * nq / sub
+    assert text.startswith(ref[:-1])                      # same bytes for the rows both produced
     assert (I[:, 0] >= 0).all() and (D[:, 0] == 0).all()          # self match at distance 0 first
     Do, Io = oracle.search_seq(xb, xq[:check], k, 1)
     exact = bool((Do == D[:check]).all() and (Io == I[:check]).all())
@@ -65,6 +80,8 @@ def run(name, xb, nq, k, batch, check):
     cpu_qps = 1024 / (time.perf_counter() - t0)
     rec = {"workload": name, "rows": n, "d": d, "dtype": str(xb.dtype), "k": k, "queries": nq, "metric": "L2",
            "seconds": dt, "qps": nq / dt, "add_seconds": t_add, "engine": st,
+           "search_self_seconds": dt_self, "search_self_qps": nq / dt_self, "search_self_identical": same,
+           "nn_json_writer_seconds": dt_write, "nn_json_reference_loop_seconds_extrapolated": dt_ref_write,
            "fallback_fraction": st["queries_exact"] / max(st["queries"], 1),
            "bit_exact_vs_oracle_first": check, "bit_exact": exact,
            "cpu_oracle_qps": cpu_qps, "cpu_threads": os.cpu_count()}
