@@ -41,6 +41,17 @@ def _worker(rank, world, port, metric, with_mask, out):
         # host arrays in -> host arrays out
         D2, I2 = idx.search(xq[:33], k, exclude=None if excl is None else excl[:33])
         np.testing.assert_array_equal(I2, I.cpu().numpy()[:33])
+        # pipelined form: several exchanges pending while later local searches run
+        xq_t = torch.from_numpy(xq).cuda()
+        ex_t = None if excl is None else torch.from_numpy(excl).cuda()
+        hs = [idx.search_async(xq_t[i * 100:(i + 1) * 100].contiguous(), k,
+                               exclude=None if ex_t is None else ex_t[i * 100:(i + 1) * 100].contiguous())
+              for i in range(3)]
+        for i, h in enumerate(hs):
+            Da, Ia = h.result()
+            torch.cuda.current_stream().synchronize()
+            np.testing.assert_array_equal(Ia.cpu().numpy(), I.cpu().numpy()[i * 100:(i + 1) * 100])
+            np.testing.assert_array_equal(Da.cpu().numpy(), D.cpu().numpy()[i * 100:(i + 1) * 100])
         out[rank] = idx.local.stats()["last_path"]
         idx.close()
     finally:

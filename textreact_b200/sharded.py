@@ -24,6 +24,25 @@ def shard_bounds(n, world, rank):
     return rank * n // world, (rank + 1) * n // world
 
 
+class PendingSearch:
+    """Handle of a ``search_async``: the merged (D, I) become valid for the caller's stream in ``result()``."""
+
+    def __init__(self, D, I, event, as_numpy):
+        self._D, self._I, self._event, self._as_numpy = D, I, event, as_numpy
+
+    def result(self):
+        D, I = self._D, self._I
+        if self._event is not None:
+            cur = torch.cuda.current_stream(D.device)
+            cur.wait_event(self._event)
+            D.record_stream(cur); I.record_stream(cur)
+            if self._as_numpy:
+                self._event.synchronize()
+        if self._as_numpy and isinstance(D, torch.Tensor):
+            return D.cpu().numpy(), I.cpu().numpy()
+        return D, I
+
+
 class ShardedIndexFlat:
     def __init__(self, d, metric, *, group=None, local_factory=None, merge_fn=None, device=None):
         self.group = group
@@ -35,6 +54,7 @@ class ShardedIndexFlat:
         self._merge = merge_fn or merge_topk
         self._ntotal_global = 0
         self._lo = 0
+        self._xstream = None          # side stream of the exchange step (CUDA only)
 
     @property
     def ntotal(self):
@@ -63,6 +83,13 @@ class ShardedIndexFlat:
 
     def search(self, xq, k, *, exclude=None, attr_below=None):
         """xq replicated on every rank.  Returns (D, I) on every rank (numpy in -> numpy out)."""
+        return self.search_async(xq, k, exclude=exclude, attr_below=attr_below).result()
+
+    def search_async(self, xq, k, *, exclude=None, attr_below=None):
+        """Local search now, exchange (all-gather + merge) queued on a side stream: the returned handle's
+        ``result()`` orders the caller's stream after it.  Calling ``search_async`` for batch i+1 before
+        ``result()`` of batch i lets the exchange of batch i -- and the wait for the slowest rank that comes
+        with it -- overlap the local search of batch i+1."""
         as_numpy = not (isinstance(xq, torch.Tensor) and xq.is_cuda)
         if as_numpy and self._on_cuda:
             # the exchange runs over NCCL: keep the per-shard lists on the device, one H2D / D2H per call
@@ -73,13 +100,23 @@ class ShardedIndexFlat:
             if exclude is not None and not (isinstance(exclude, torch.Tensor) and exclude.is_cuda):
                 exclude = torch.as_tensor(np.ascontiguousarray(exclude, dtype=np.int32)).to(dev)
         kw = {} if attr_below is None else {"attr_below": attr_below}
-        D, I = self.local.search(xq, k, exclude=exclude, **kw)
+        D, I = self.local.search(xq, k, exclude=exclude, **kw)       # complete on return (host-synchronised)
         if not isinstance(D, torch.Tensor):
             D, I = torch.from_numpy(D), torch.from_numpy(I)
-        Dm, Im = self.exchange(D, I)
-        if as_numpy and isinstance(Dm, torch.Tensor):
-            return Dm.cpu().numpy(), Im.cpu().numpy()
-        return Dm, Im
+        if not D.is_cuda:                                              # CPU test doubles: nothing to overlap
+            Dm, Im = self.exchange(D, I)
+            return PendingSearch(Dm, Im, None, as_numpy)
+        if self._xstream is None:
+            self._xstream = torch.cuda.Stream(device=D.device)
+        cur = torch.cuda.current_stream(D.device)
+        self._xstream.wait_stream(cur)
+        with torch.cuda.stream(self._xstream):
+            Dm, Im = self.exchange(D, I)
+            ev = torch.cuda.Event()
+            ev.record(self._xstream)
+        for t in (D, I):
+            t.record_stream(self._xstream)
+        return PendingSearch(Dm, Im, ev, as_numpy)
 
     def exchange(self, D, I):
         """The one exchange step: all-gather the per-shard [nq, k] lists, k-way merge (K5) on every rank."""
