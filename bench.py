@@ -294,23 +294,15 @@ def main():
         return ms
 
     # ---- device-resident throughput ---------------------------------------------------------------
-    # N > 1: the exchange of step i (all-gather + merge, and the wait for the slowest rank) is left pending while
-    # the local search of step i+1 runs; every step's merged result is complete before the timed region ends.
-    pending = [None]
-
+    # N > 1: the exchange (all-gather + merge) of a step completes before the next step starts.  Leaving it pending on a
+    # side stream while the next local search runs (ShardedIndexFlat.search_async) was measured SLOWER (93 vs 72 ms per
+    # step at N = 2): the NCCL kernel of rank A takes SMs and spins for rank B, whose own NCCL kernel is queued behind its
+    # persistent, statically partitioned K2 -- the displaced K2 CTAs of A then run their whole share late.
     def step_dev(i):
-        if sidx is None:
-            index.search(queries[i % len(queries)], K)
-            return
-        h = sidx.search_async(queries[i % len(queries)], K)
-        if pending[0] is not None:
-            pending[0].result()
-        pending[0] = h
+        index.search(queries[i % len(queries)], K)
 
     def drain():
-        if pending[0] is not None:
-            pending[0].result()
-            pending[0] = None
+        pass
 
     for i in range(args.warmup):
         step_dev(i)
@@ -420,8 +412,7 @@ def main():
                           "dist": "iid N(0,1) fp32, seeds 1234+rank / 4321", "l2_policy": "inputs_exceed_l2 "
                           f"(bf16 corpus shard {2 * (hi - lo) * D_MODEL / 1e9:.1f} GB >> 126 MB L2)",
                           "scored_pairs_per_s": qps * rows,
-                          "exchange": None if world == 1 else "all-gather + merge of step i pending on a side stream "
-                                      "while step i+1 searches locally (search_async); complete inside the timed region"},
+                          "exchange": None if world == 1 else "NCCL all-gather + device merge after every local search"},
                "clocks": clocks,
                "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": batch * D_MODEL * 4,
                        "d2h_bytes_per_step": batch * K * 12, "ms_per_step": ms_e2e_dev / args.steps,

@@ -89,7 +89,13 @@ class ShardedIndexFlat:
         """Local search now, exchange (all-gather + merge) queued on a side stream: the returned handle's
         ``result()`` orders the caller's stream after it.  Calling ``search_async`` for batch i+1 before
         ``result()`` of batch i lets the exchange of batch i -- and the wait for the slowest rank that comes
-        with it -- overlap the local search of batch i+1."""
+        with it -- overlap the local search of batch i+1.
+
+        Measured caveat (2 x B200, 16M rows, batch 8192): with the current K2 -- persistent, one CTA per SM, corpus
+        tiles statically assigned -- this is slower than the synchronous ``search`` (93 vs 72 ms per step): the NCCL
+        kernel takes SMs and spins for the peer whose own NCCL kernel is queued behind its K2, and the displaced K2
+        CTAs then run their whole static share late.  It pays only where the local search leaves SMs free (small
+        corpora, exact path); a dynamic tile scheduler in K2 is what would make it pay in general."""
         as_numpy = not (isinstance(xq, torch.Tensor) and xq.is_cuda)
         if as_numpy and self._on_cuda:
             # the exchange runs over NCCL: keep the per-shard lists on the device, one H2D / D2H per call
