@@ -368,12 +368,20 @@ def main():
 
         def exchange(i):
             sidx.exchange(Dl, Il)
-        for i in range(3):
-            exchange(i)
-        ex_ms = timed(exchange, 10) / 10
+        mode = sidx._exchange_mode
+        ex_ms = {}
+        for m in ([mode, "nccl"] if mode == "peer" else [mode]):      # the mode in use, and NCCL beside it
+            sidx._exchange_mode = m
+            for i in range(3):
+                exchange(i)
+            ex_ms[m] = timed(exchange, 10) / 10
+        sidx._exchange_mode = mode
         multi = {"local_ms_per_rank": [round(float(v), 3) for v in allr[:, 0].tolist()],
                  "k2_ms_per_rank": [round(float(v), 3) for v in allr[:, 1].tolist()],
-                 "exchange_ms": ex_ms, "exchange": "NCCL all-gather of per-shard (D, I) + device k-way merge"}
+                 "exchange_mode": mode, "exchange_ms": ex_ms[mode], "exchange_ms_by_mode": ex_ms,
+                 "exchange": {"peer": "ONE kernel: all-gather fused into the k-way merge over NVLink peer memory "
+                                      "(CUDA IPC export buffers, flag protocol, no NCCL in the data path)",
+                              "nccl": "NCCL all-gather of per-shard (D, I) + device k-way merge"}[mode]}
 
     kern_ms = sum(pre_ms) / len(pre_ms)
     flops = 2.0 * batch * (hi - lo) * D_MODEL
@@ -412,7 +420,8 @@ def main():
                           "dist": "iid N(0,1) fp32, seeds 1234+rank / 4321", "l2_policy": "inputs_exceed_l2 "
                           f"(bf16 corpus shard {2 * (hi - lo) * D_MODEL / 1e9:.1f} GB >> 126 MB L2)",
                           "scored_pairs_per_s": qps * rows,
-                          "exchange": None if world == 1 else "NCCL all-gather + device merge after every local search"},
+                          "exchange": None if world == 1 else f"{sidx._exchange_mode} exchange after every local search "
+                                      "(peer = gather fused into the merge kernel over NVLink peer memory)"},
                "clocks": clocks,
                "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": batch * D_MODEL * 4,
                        "d2h_bytes_per_step": batch * K * 12, "ms_per_step": ms_e2e_dev / args.steps,

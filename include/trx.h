@@ -15,8 +15,9 @@
  *   trx_search_self <- train->train search (queries are the corpus)  retrieve/retrieve_faiss.py:114-115
  *   trx_reset / trx_destroy <- lifetime of the index object built per split
  *                                                     retrieve/retrieve_faiss.py:62-74
- *   trx_merge_topk  <- (no reference counterpart) k-way merge of per-shard results for
- *                      the row-sharded multi-GPU mode
+ *   trx_merge_topk, trx_exchange_* <- (no reference counterpart) k-way merge of per-shard results for
+ *                      the row-sharded multi-GPU mode: after an NCCL all-gather,
+ *                      or fused with the gather over NVLink peer memory
  *
  * Conventions
  *   - plain C, no C++ types, no exceptions, never abort(): every call returns an int
@@ -145,6 +146,22 @@ int trx_stats(const trx_index* idx, trx_stats_t* out);
  * Dg: float[G*nq*k], Ig: int64[G*nq*k], shard-major.  Device pointers, stream-ordered. */
 int trx_merge_topk(int metric, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k,
                    float* D, int64_t* I, void* cuda_stream);
+
+/* The exchange step of the row-sharded mode as one kernel over NVLink peer memory (one process per GPU, one node):
+ * every rank exports a buffer through CUDA IPC, maps the buffers of its peers, and the all-gather of the per-shard
+ * lists is fused into the merge kernel (peer loads; a flag protocol over peer stores replaces NCCL).
+ *   create  -> allocate this rank's export buffer for up to max_entries = nq*k results per exchange
+ *   handle  -> its 64-byte CUDA IPC handle (exchange the handles of all ranks by any means, in rank order)
+ *   connect -> map the peers (handles: world*64 bytes)
+ *   merge   -> collective: every rank passes its local [nq,k] lists (device pointers, best first, global ids) and
+ *              receives the merged top-k; stream-ordered, no host synchronisation. */
+typedef struct trx_exchange trx_exchange;
+int trx_exchange_create(int device, int rank, int world, int64_t max_entries, trx_exchange** out);
+int trx_exchange_handle(trx_exchange* ex, unsigned char* handle64);
+int trx_exchange_connect(trx_exchange* ex, const unsigned char* handles);
+int trx_exchange_merge(trx_exchange* ex, int metric, const float* D_local, const int64_t* I_local, int64_t nq, int k,
+                       float* D, int64_t* I, void* cuda_stream);
+void trx_exchange_destroy(trx_exchange* ex);
 
 /* Raw bf16 scoring GEMM on the tcgen05 path, for tests and profiling:
  * out[nq, n] = bf16(xq) . bf16(x_row)  (fp32 accumulate) over rows [row0, row0+n). */

@@ -1,6 +1,7 @@
-"""GPU, world_size 2, NCCL: the row-sharded search on the real engine --
-local exact top-k per shard with global ids, all-gather over NVLink, device k-way merge (K5) --
-must equal the unsharded answer.  Skipped on a one-GPU box (the gloo test covers the host logic)."""
+"""GPU, world_size 2: the row-sharded search on the real engine -- local exact top-k per
+shard with global ids, then the exchange, either fused (all-gather inside the merge kernel over NVLink peer
+memory, CUDA IPC + flag protocol, K5p) or NCCL all-gather + device k-way merge (K5) -- must equal the unsharded
+answer.  Skipped on a one-GPU box (the gloo test covers the host logic)."""
 import os
 import sys
 
@@ -11,11 +12,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, metric, with_mask, out):
+def _worker(rank, world, port, metric, with_mask, exchange, out):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TRX_EXCHANGE_ENTRIES="1000")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -26,7 +27,7 @@ def _worker(rank, world, port, metric, with_mask, out):
         xb, xq = util.gaussian(n, d, 5), util.gaussian(nq, d, 6)
         groups = (np.arange(n) // 4).astype(np.int32)
         excl = groups[np.random.default_rng(7).integers(0, n, nq)].astype(np.int32) if with_mask else None
-        idx = ShardedIndexFlat(d, metric, device=rank)
+        idx = ShardedIndexFlat(d, metric, device=rank, exchange=exchange)
         idx.add_global(xb)
         lo, hi = shard_bounds(n, world, rank)
         assert idx.local.ntotal == hi - lo and idx.ntotal == n
@@ -52,23 +53,29 @@ def _worker(rank, world, port, metric, with_mask, out):
             torch.cuda.current_stream().synchronize()
             np.testing.assert_array_equal(Ia.cpu().numpy(), I.cpu().numpy()[i * 100:(i + 1) * 100])
             np.testing.assert_array_equal(Da.cpu().numpy(), D.cpu().numpy()[i * 100:(i + 1) * 100])
+        assert idx._exchange_mode == exchange, "peer mapping failed: fell back to NCCL"
+        # a larger exchange than the export buffers were sized for: they are rebuilt collectively
+        if exchange == "peer":
+            Db, Ib = idx.search(xq_t[:500].contiguous(), 256)
+            oracle.check_parity(Db.cpu().numpy()[:20], Ib.cpu().numpy()[:20], xb, xq[:20], 256, metric)
         out[rank] = idx.local.stats()["last_path"]
         idx.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("metric,with_mask", [(0, False), (1, False), (0, True)])
-def test_two_gpu_sharded_search_equals_unsharded(metric, with_mask):
+def test_two_gpu_sharded_search_equals_unsharded(metric, with_mask, exchange):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world = 2
-    port = 29900 + os.getpid() % 300 + metric * 7 + int(with_mask)
+    port = 29900 + os.getpid() % 300 + metric * 7 + int(with_mask) + (13 if exchange == "peer" else 0)
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, metric, with_mask, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, metric, with_mask, exchange, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

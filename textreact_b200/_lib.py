@@ -51,6 +51,11 @@ SIGNATURES = {
     "trx_get_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "trx_stats": (ctypes.c_int, [_vp, ctypes.POINTER(TrxStats)]),
     "trx_merge_topk": (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
+    "trx_exchange_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(_vp)]),
+    "trx_exchange_handle": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "trx_exchange_connect": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "trx_exchange_merge": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
+    "trx_exchange_destroy": (None, [_vp]),
     "trx_debug_scores_umma": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _vp, _vp]),
     "trx_last_error": (ctypes.c_char_p, []),
     "trx_version": (ctypes.c_char_p, []),

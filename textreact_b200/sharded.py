@@ -16,7 +16,11 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .index import IndexFlat, merge_topk
+import ctypes
+import os
+
+from . import _lib
+from .index import IndexFlat, _stream_handle, merge_topk
 
 
 def shard_bounds(n, world, rank):
@@ -44,7 +48,7 @@ class PendingSearch:
 
 
 class ShardedIndexFlat:
-    def __init__(self, d, metric, *, group=None, local_factory=None, merge_fn=None, device=None):
+    def __init__(self, d, metric, *, group=None, local_factory=None, merge_fn=None, device=None, exchange=None):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -55,6 +59,11 @@ class ShardedIndexFlat:
         self._ntotal_global = 0
         self._lo = 0
         self._xstream = None          # side stream of the exchange step (CUDA only)
+        # "peer": all-gather fused into the merge kernel over NVLink peer memory (CUDA IPC, K5p); "nccl": NCCL
+        # all-gather + K5.  Default: peer on the CUDA engine, NCCL for the CPU test doubles / when mapping fails.
+        self._exchange_mode = exchange or os.environ.get("TRX_EXCHANGE") or ("peer" if self._on_cuda and merge_fn is None else "nccl")
+        self._peer = None             # trx_exchange handle
+        self._peer_entries = 0
 
     @property
     def ntotal(self):
@@ -124,8 +133,50 @@ class ShardedIndexFlat:
             t.record_stream(self._xstream)
         return PendingSearch(Dm, Im, ev, as_numpy)
 
+    def _peer_exchange(self, nq, k, device):
+        """(Re)build the peer-memory exchange for at least nq*k entries.  Collective: every rank takes the same
+        decisions (queries are replicated, so nq and k agree).  Returns None when peers cannot be mapped."""
+        need = int(nq) * int(k)
+        if self._peer is not None and need <= self._peer_entries:
+            return self._peer
+        L = _lib.lib()
+        if self._peer is not None:
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)          # nobody still reads the old export buffers
+            L.trx_exchange_destroy(self._peer)
+            self._peer = None
+        entries = max(need, int(os.environ.get("TRX_EXCHANGE_ENTRIES", 8192 * 100)))
+        ex = ctypes.c_void_p()
+        ok = L.trx_exchange_create(device.index, self.rank, self.world, entries, ctypes.byref(ex)) == 0
+        handle = ctypes.create_string_buffer(64)
+        ok = ok and L.trx_exchange_handle(ex, handle) == 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw) if ok else None, group=self.group)
+        ok = ok and all(h is not None for h in handles)
+        ok = ok and L.trx_exchange_connect(ex, b"".join(handles)) == 0
+        flag = torch.tensor([1 if ok else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:                   # some rank could not map its peers: everybody uses NCCL
+            if ex:
+                L.trx_exchange_destroy(ex)
+            self._exchange_mode = "nccl"
+            return None
+        self._peer, self._peer_entries = ex, entries
+        return ex
+
     def exchange(self, D, I):
-        """The one exchange step: all-gather the per-shard [nq, k] lists, k-way merge (K5) on every rank."""
+        """The one exchange step: the per-shard [nq, k] lists of every rank -> the merged top-k on every rank.
+        CUDA default: ONE kernel that gathers over NVLink peer memory and merges (K5p, k5_peer.cu);
+        otherwise all-gather (NCCL / gloo) + k-way merge (K5)."""
+        if D.is_cuda and self._exchange_mode == "peer" and self.world > 1:
+            ex = self._peer_exchange(D.shape[0], D.shape[1], D.device)
+            if ex is not None:
+                D, I = D.contiguous(), I.contiguous()
+                Dm, Im = torch.empty_like(D), torch.empty_like(I)
+                _lib.check(_lib.lib().trx_exchange_merge(ex, self.metric_type, D.data_ptr(), I.data_ptr(), D.shape[0],
+                                                         D.shape[1], Dm.data_ptr(), Im.data_ptr(),
+                                                         _stream_handle(D.device)), "exchange_merge")
+                return Dm, Im
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
         Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
         if D.is_cuda:     # NCCL: one ncclAllGather each, straight into the [G, nq, k] buffers
@@ -137,5 +188,8 @@ class ShardedIndexFlat:
         return self._merge(Dg, Ig, self.metric_type)
 
     def close(self):
+        if self._peer is not None:
+            _lib.lib().trx_exchange_destroy(self._peer)
+            self._peer = None
         if hasattr(self.local, "close"):
             self.local.close()
