@@ -71,11 +71,14 @@ __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView
                                                             unsigned long long want, int G, int64_t nq, int k,
                                                             float* __restrict__ D, int64_t* __restrict__ I) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
     const int64_t q = blockIdx.x;
     const int total = G * k;
     int P = 2;
     while (P < total) P <<= 1;
+    // layout: keys[P] u64 | ids[total] i64 | scores[total] f32   (every peer entry crosses NVLink exactly once)
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    int64_t* sI = reinterpret_cast<int64_t*>(keys + P);
+    float* sD = reinterpret_cast<float*>(sI + total);
     // wait for every rank's publish of this exchange (flags live in LOCAL memory; peers store into them)
     if (threadIdx.x < G) {
         while (ld_acquire_sys(my_flags + threadIdx.x) < want) __nanosleep(64);
@@ -87,10 +90,9 @@ __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView
             const int g = i / k, j = i - g * k;
             const int64_t src = q * k + j;
             const int64_t id = *reinterpret_cast<const volatile int64_t*>(pv.I[g] + src);     // peer load over NVLink
-            if (id >= 0) {
-                const float v = *reinterpret_cast<const volatile float*>(pv.D[g] + src);
-                key = pack_key(metric == TRX_METRIC_L2 ? -v : v, (uint32_t)i);
-            }
+            const float v = *reinterpret_cast<const volatile float*>(pv.D[g] + src);
+            sI[i] = id; sD[i] = v;
+            if (id >= 0) key = pack_key(metric == TRX_METRIC_L2 ? -v : v, (uint32_t)i);
         }
         keys[i] = key;
     }
@@ -101,10 +103,8 @@ __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView
         if (key == KEY_SENTINEL) { D[q * k + j] = fill; I[q * k + j] = -1; }
         else {
             const int pos = (int)key_id(key);
-            const int g = pos / k, jj = pos - g * k;
-            const int64_t src = q * k + jj;
-            D[q * k + j] = *reinterpret_cast<const volatile float*>(pv.D[g] + src);
-            I[q * k + j] = *reinterpret_cast<const volatile int64_t*>(pv.I[g] + src);
+            D[q * k + j] = sD[pos];
+            I[q * k + j] = sI[pos];
         }
     }
 }
@@ -219,7 +219,7 @@ int trx_exchange_merge(trx_exchange* ex, int metric, const float* D_local, const
     const int64_t total = (int64_t)ex->world * k;
     int P = 2;
     while (P < total) P <<= 1;
-    const size_t smem = (size_t)P * 8;
+    const size_t smem = (size_t)P * 8 + (size_t)total * 12;
     if (smem > 200 * 1024) { set_error("exchange: world*k=%lld too large", (long long)total); return TRX_EINVAL; }
     TRX_CUDA(cudaFuncSetAttribute(k5_peer_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k5_peer_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(metric, pv, reinterpret_cast<const unsigned long long*>(ex->base),
