@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -194,8 +194,8 @@ def emit(obj):
 
 def main():
     import faulthandler
-    wd = float(os.environ.get("TRX_BENCH_WATCHDOG", "0"))
-    if wd > 0:   # dump every thread's stack and exit if the run is still alive after `wd` seconds
+    wd = float(os.environ.get("TRX_BENCH_WATCHDOG", "900"))
+    if wd > 0:   # dump every thread's stack and exit if the run is still alive after `wd` seconds (0 disables)
         faulthandler.dump_traceback_later(wd, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
