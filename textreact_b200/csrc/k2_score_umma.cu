@@ -533,10 +533,13 @@ template <int MODE, bool PAIR, int AR>
 int launch_mode(const CUtensorMap& mq, const CUtensorMap& mx, const KParams& p, int grid, cudaStream_t st) {
     auto kern = k2_umma_kernel<MODE, PAIR, AR>;
     using C = Cfg<PAIR, AR>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // per device (an attribute set on one device does not carry to another one used by the same process)
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    TRX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
