@@ -82,3 +82,27 @@ def test_two_gpu_sharded_search_equals_unsharded(metric, with_mask, exchange):
         p.join(300)
         assert p.exitcode == 0
     assert len(out) == world
+
+
+def test_two_devices_in_one_process():
+    """Indexes on different GPUs of the same process (the C ABI takes a device ordinal; per-device kernel
+    attributes, device guards around every call)."""
+    import torch
+    import textreact_b200 as trx
+    from oracle import cpu_flat as oracle
+    from tests import util
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    xb, xq = util.gaussian(30000, 256, 301), util.gaussian(200, 256, 302)
+    res = []
+    for dev in (0, 1):
+        idx = trx.IndexFlatIP(256, device=dev)
+        idx.add(xb)
+        res.append(idx.search(xq, 10))                                   # numpy in / out, current device stays 0
+        Dt, It = idx.search(torch.from_numpy(xq).to(f"cuda:{dev}"), 10)    # tensors on the index's device
+        assert It.device.index == dev
+        np.testing.assert_array_equal(It.cpu().numpy(), res[-1][1])
+        idx.close()
+    assert torch.cuda.current_device() == 0
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    oracle.check_parity(res[0][0], res[0][1], xb, xq, 10, 0)
