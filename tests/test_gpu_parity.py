@@ -511,3 +511,37 @@ def test_modes_without_their_side_data_are_errors():
     D, I = idx.search(xb[:3], 4)                 # the failed calls left no option behind
     assert (I[:, 0] == np.arange(3)).all()
     idx.close()
+
+
+def test_cuda_graph_replay_matches_plain_launches():
+    """Small batches replay their kernel pipeline as one cached CUDA graph: same answers as plain launches, for
+    changing query contents, after the index grows, with the mask on and off, on both prefilter paths."""
+    trx = _engine()
+    n, d, k = 30000, 128, 10
+    xb = util.gaussian(n + 5000, d, 241)
+    groups = (np.arange(n + 5000) // 3).astype(np.int32)
+    idx = trx.IndexFlatIP(d)
+    idx.add(xb[:n])
+    idx.set_groups(groups[:n])
+    assert idx.get_option("graphs") == 1
+    for path, nq in ((trx.PATH_UMMA, 40), (trx.PATH_STREAM, 1), (trx.PATH_UMMA, 200)):
+        idx.set_option("path", path)
+        for rep in range(3):                               # the second and third call replay the cached graph
+            xq = util.gaussian(nq, d, 250 + rep)
+            excl = groups[np.random.default_rng(rep).integers(0, n, nq)] if rep == 2 else None
+            idx.set_option("graphs", 1)
+            D1, I1 = idx.search(xq, k, exclude=excl)
+            idx.set_option("graphs", 0)
+            D0, I0 = idx.search(xq, k, exclude=excl)
+            np.testing.assert_array_equal(I1, I0); np.testing.assert_array_equal(D1, D0)
+            oracle.check_parity(D1, I1, xb[:n], xq, k, IP, groups[:n] if excl is not None else None, excl)
+    idx.set_option("graphs", 1)
+    idx.set_option("path", trx.PATH_UMMA)
+    xq = util.gaussian(40, d, 260)
+    idx.search(xq, k)
+    idx.add(xb[n:])                                        # buffers move, ntotal changes: the graph must not be reused
+    D, I = idx.search(xq, k)
+    oracle.check_parity(D, I, xb, xq, k, IP)
+    st = idx.stats()
+    assert st["launches"] > 0
+    idx.close()

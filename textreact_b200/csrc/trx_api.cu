@@ -15,6 +15,7 @@
 #include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -102,6 +103,10 @@ struct BatchWs {
     uint32_t* h_nfb = nullptr;                             // pinned: fallback count of this batch
     float* hD = nullptr; int64_t* hI = nullptr; size_t h_elems = 0;   // pinned staging for pageable outputs
     cudaEvent_t q_ready = nullptr, done = nullptr, ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // launch plan of the prefilter pipeline (prepare_prefilter) and its cached CUDA graph (small batches)
+    bool pair = false; int S = 0, T = 0, r = 0, log_cap = 0;
+    cudaGraphExec_t graph = nullptr; int graph_nodes = 0; uint64_t graph_gen = 0; int64_t graph_B = -1; int graph_k = 0, graph_path = 0;
+    bool graph_excl = false;
     // the batch in flight
     int64_t B = 0; int path = 0;
     const float* qdev = nullptr; const int32_t* exdev = nullptr;
@@ -137,6 +142,9 @@ struct trx_index {
     int umma_pair = 1;      // allow the CTA-pair (cta_group::2) tiling
     int pair_min_batch = 129;  // ... for batches of at least this many queries (measured crossover)
     int pipeline = 1;       // overlap the upload / launch of batch i+1 with batch i when a call has several
+    int graphs = 1;         // replay the prefilter pipeline of small batches (<= graph_max_batch) as one CUDA graph
+    int graph_max_batch = 256;
+    uint64_t gen = 1;       // bumped by everything that changes what a captured graph would do
     float thr_bias = 0.f;   // experiments only: added to every estimated threshold
     BatchWs ws[2];
     // fallback-only buffers (fallbacks run synchronously, one batch at a time)
@@ -161,6 +169,7 @@ static void free_batch_ws(BatchWs& w) {
     if (w.q_ready) { cudaEventDestroy(w.q_ready); w.q_ready = nullptr; }
     if (w.done) { cudaEventDestroy(w.done); w.done = nullptr; }
     for (int i = 0; i < 4; i++) if (w.ev[i]) { cudaEventDestroy(w.ev[i]); w.ev[i] = nullptr; }
+    if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; w.graph_B = -1; }
     w.batch = w.cap = w.k = 0; w.slots_elems = w.hitlog_elems = w.h_elems = 0; w.hitlog_n = 0;
 }
 
@@ -268,9 +277,10 @@ static int ensure_ws(trx_index* ix, BatchWs& w, int B, int k, int cap) {
         TRX_TRY(dmalloc(&w.cand_cnt, (size_t)nb));
         TRX_TRY(dmalloc(&w.fb_list, (size_t)nb));
         TRX_TRY(dmalloc(&w.fb_thr, (size_t)nb));
-        w.batch = nb; w.cap = nc;
+        w.batch = nb; w.cap = nc; ix->gen++;
     }
     if (k > w.k) {
+        ix->gen++;
         dfree(w.Dd); dfree(w.Id);
         TRX_TRY(dmalloc(&w.Dd, (size_t)w.batch * k));
         TRX_TRY(dmalloc(&w.Id, (size_t)w.batch * k));
@@ -304,6 +314,7 @@ static int ensure_sample(trx_index* ix, cudaStream_t st) {
     ix->ns = ns;
     TRX_TRY(launch_sample_gather(ix->x16, ix->ntotal, ix->Kp, ix->sample_rate, ix->xs16, ns, st));
     ix->sample_dirty = false;
+    ix->gen++;
     return TRX_OK;
 }
 
@@ -406,6 +417,73 @@ static int send_results(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
     return TRX_OK;
 }
 
+// Sizes every buffer the prefilter pipeline of batch w needs and fixes its launch plan (no stream work here, so
+// that enqueue_prefilter can run inside a stream capture).
+static int prepare_prefilter(trx_index* ix, BatchWs& w, int k) {
+    const int64_t B = w.B, N = ix->ntotal;
+    w.T = effective_target(ix, k);
+    w.r = std::max(1, (w.T + ix->sample_rate / 2) / ix->sample_rate);
+    w.pair = ix->umma_pair && B >= ix->pair_min_batch;
+    w.S = umma_num_slices(ix->ns, B, ix->sm_count, w.pair);
+    size_t need = (size_t)B * w.S * 32;
+    if (need > w.slots_elems) { dfree(w.slots); TRX_TRY(dmalloc(&w.slots, need)); w.slots_elems = need; ix->gen++; }
+    if (w.path == TRX_PATH_UMMA) {   // private hit logs: 3x the expected hits per epilogue thread, at least 256 entries
+        const int grid = umma_grid(B, N, ix->sm_count, w.pair, false);
+        const int nlogs = grid * 128;
+        double expect = 1.15 * (double)B * (double)w.T / (double)nlogs;
+        w.log_cap = std::max(256, (int)(3.0 * expect) + 64);
+        size_t need_l = (size_t)nlogs * w.log_cap;
+        if (need_l > w.hitlog_elems || nlogs > w.hitlog_n) {
+            dfree(w.hitlog); dfree(w.hitlog_cnt);
+            TRX_TRY(dmalloc(&w.hitlog, need_l));
+            TRX_TRY(dmalloc(&w.hitlog_cnt, (size_t)nlogs));
+            w.hitlog_elems = need_l; w.hitlog_n = nlogs; ix->gen++;
+        }
+    }
+    return TRX_OK;
+}
+
+// The prefilter pipeline of one batch, stream work only:
+//   K1 batch begin -> K2<SLOTMAX> on the sample -> thresholds -> main pass (K2<THRESH> + scatter | K3) -> K4 -> count
+static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
+    const int64_t B = w.B, N = ix->ntotal;
+    TRX_TRY(launch_query_prep(w.qdev, B, ix->d, ix->Kp, ix->metric, w.q16, w.qnorm2, ix->norm2_max, w.eps,
+                              w.eps_acc, w.cand_cnt, w.fb_count, st));
+    // pass 0 (both prefilter paths): tcgen05 scores of the batch against the 1/32 row sample, slot maxima,
+    // r-th largest -> per-query threshold that ~T corpus rows are expected to beat
+    UmmaArgs u{};
+    u.q16 = w.q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
+    u.pair = w.pair;
+    u.mode = 2; u.out = w.slots;
+    TRX_TRY(launch_umma(u, ix->sm_count, st));
+    TRX_TRY(launch_slot_thr(w.slots, B, w.S, std::min(w.r, 32 * w.S), w.thr, st));
+    if (ix->thr_bias != 0.f) {
+        add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.thr, (int)B, ix->thr_bias);
+        count_launch();
+    }
+    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[1], st));
+
+    if (w.path == TRX_PATH_UMMA) {
+        u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
+        u.thr = w.thr; u.cand = w.cand; u.cand_cnt = w.cand_cnt; u.cap = w.cap;
+        u.log = w.hitlog; u.log_cnt = w.hitlog_cnt; u.log_cap = w.log_cap;
+        TRX_TRY(launch_umma(u, ix->sm_count, st));
+    } else {
+        // main pass on the CUDA cores: one sweep over the bf16 corpus per 4 queries, hits appended directly
+        StreamArgs a{};
+        a.x = ix->x16; a.pitch = ix->Kp; a.n = N; a.d = ix->Kp;
+        a.q16 = w.q16; a.q_pitch = ix->Kp; a.nq = B;
+        a.metric = TRX_METRIC_INNER_PRODUCT; a.bf16 = true; a.append = true;
+        a.thr = w.thr; a.cand = w.cand; a.cand_cnt = w.cand_cnt; a.cap = w.cap;
+        TRX_TRY(launch_stream(a, ix->sm_count, st));
+    }
+    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[2], st));
+
+    TRX_TRY(launch_rescore(rescore_args(ix, w, k), st));
+    TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
+    return TRX_OK;
+}
+
 // Queue one batch: query upload (copy stream), every kernel, the fallback count and the results (compute
 // stream).  Nothing here waits for the GPU.
 static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev, int64_t B, int k, const int32_t* excl,
@@ -456,59 +534,55 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
         *w.h_nfb = 0;
     } else {
         TRX_TRY(ensure_sample(ix, st));
-        TRX_TRY(launch_query_prep(w.qdev, B, ix->d, ix->Kp, ix->metric, w.q16, w.qnorm2, ix->norm2_max, w.eps,
-                                  w.eps_acc, w.cand_cnt, w.fb_count, st));
-        const int T = effective_target(ix, k);
-        int r = std::max(1, (T + ix->sample_rate / 2) / ix->sample_rate);
-
-        // pass 0 (both prefilter paths): tcgen05 scores of the batch against the 1/32 row sample, slot maxima,
-        // r-th largest -> per-query threshold that ~T corpus rows are expected to beat
-        UmmaArgs u{};
-        u.q16 = w.q16; u.nq = B; u.x16 = ix->xs16; u.n = ix->ns; u.Kp = ix->Kp;
-        u.pair = ix->umma_pair && B >= ix->pair_min_batch;
-        const int S = umma_num_slices(ix->ns, B, ix->sm_count, u.pair);
-        size_t need = (size_t)B * S * 32;
-        if (need > w.slots_elems) { dfree(w.slots); TRX_TRY(dmalloc(&w.slots, need)); w.slots_elems = need; }
-        u.mode = 2; u.out = w.slots;
-        TRX_TRY(launch_umma(u, ix->sm_count, st));
-        TRX_TRY(launch_slot_thr(w.slots, B, S, std::min(r, 32 * S), w.thr, st));
-        if (ix->thr_bias != 0.f) {
-            add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.thr, (int)B, ix->thr_bias);
-            count_launch();
-        }
-        if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[1], st));
-
-        if (path == TRX_PATH_UMMA) {
-            u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
-            u.thr = w.thr; u.cand = w.cand; u.cand_cnt = w.cand_cnt; u.cap = w.cap;
-            {   // private hit logs: 3x the expected hits per epilogue thread, at least 256 entries
-                const int grid = umma_grid(B, N, ix->sm_count, u.pair, false);
-                const int nlogs = grid * 128;
-                double expect = 1.15 * (double)B * (double)T / (double)nlogs;
-                int log_cap = std::max(256, (int)(3.0 * expect) + 64);
-                size_t need_l = (size_t)nlogs * log_cap;
-                if (need_l > w.hitlog_elems || nlogs > w.hitlog_n) {
-                    dfree(w.hitlog); dfree(w.hitlog_cnt);
-                    TRX_TRY(dmalloc(&w.hitlog, need_l));
-                    TRX_TRY(dmalloc(&w.hitlog_cnt, (size_t)nlogs));
-                    w.hitlog_elems = need_l; w.hitlog_n = nlogs;
-                }
-                u.log = w.hitlog; u.log_cnt = w.hitlog_cnt; u.log_cap = log_cap;
+        TRX_TRY(prepare_prefilter(ix, w, k));
+        bool replayed = false;
+        // Small batches are launch-latency sensitive: the pipeline of a given (batch size, k, path) is captured once
+        // and replayed as one graph.  Not on the legacy / NULL stream (not capturable) and not while timing.
+        if (ix->graphs && B <= ix->graph_max_batch && !ix->timing && st != nullptr && st != cudaStreamLegacy &&
+            st != cudaStreamPerThread) {
+            // the graph reads its inputs from the workspace: bring device-resident inputs there first
+            if (w.qdev != w.q32) {
+                TRX_CUDA(cudaMemcpyAsync(w.q32, w.qdev, (size_t)B * ix->d * 4, cudaMemcpyDeviceToDevice, st));
+                w.qdev = w.q32;
             }
-            TRX_TRY(launch_umma(u, ix->sm_count, st));
-        } else {
-            // main pass on the CUDA cores: one sweep over the bf16 corpus per 4 queries, hits appended directly
-            StreamArgs a{};
-            a.x = ix->x16; a.pitch = ix->Kp; a.n = N; a.d = ix->Kp;
-            a.q16 = w.q16; a.q_pitch = ix->Kp; a.nq = B;
-            a.metric = TRX_METRIC_INNER_PRODUCT; a.bf16 = true; a.append = true;
-            a.thr = w.thr; a.cand = w.cand; a.cand_cnt = w.cand_cnt; a.cap = w.cap;
-            TRX_TRY(launch_stream(a, ix->sm_count, st));
+            if (w.exdev != nullptr && w.exdev != w.excl) {
+                TRX_CUDA(cudaMemcpyAsync(w.excl, w.exdev, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+                w.exdev = w.excl;
+            }
+            const bool hit = w.graph != nullptr && w.graph_gen == ix->gen && w.graph_B == B && w.graph_k == k &&
+                             w.graph_path == path && w.graph_excl == (w.exdev != nullptr);
+            if (!hit) {
+                if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+                cudaGraph_t g = nullptr;
+                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int64_t l0 = g_launches.load();
+                    int rc = enqueue_prefilter(ix, w, k, st);
+                    cudaError_t e = cudaStreamEndCapture(st, &g);
+                    w.graph_nodes = (int)(g_launches.load() - l0);
+                    if (rc == TRX_OK && e == cudaSuccess && g != nullptr &&
+                        cudaGraphInstantiate(&w.graph, g, 0) == cudaSuccess) {
+                        w.graph_gen = ix->gen; w.graph_B = B; w.graph_k = k; w.graph_path = path;
+                        w.graph_excl = w.exdev != nullptr;
+                        count_launch(-w.graph_nodes);      // captured, not launched
+                    } else {
+                        w.graph = nullptr;
+                        ix->graphs = 0;                    // capture is not possible here: plain launches from now on
+                        count_launch(-w.graph_nodes);
+                    }
+                    if (g) cudaGraphDestroy(g);
+                    cudaGetLastError();
+                } else {
+                    cudaGetLastError();
+                    ix->graphs = 0;
+                }
+            }
+            if (w.graph != nullptr) {
+                TRX_CUDA(cudaGraphLaunch(w.graph, st));
+                count_launch(w.graph_nodes);
+                replayed = true;
+            }
         }
-        if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[2], st));
-
-        TRX_TRY(launch_rescore(rescore_args(ix, w, k), st));
-        TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
+        if (!replayed) TRX_TRY(enqueue_prefilter(ix, w, k, st));
     }
     // Common case (every query certified): the results leave with the same synchronisation that reads the
     // fallback count.  Otherwise finish_batch fills the missing rows and sends them again.
@@ -643,6 +717,7 @@ int trx_create(int d, int metric, int device, trx_index** out) {
     trx_index* ix = new (std::nothrow) trx_index();
     if (!ix) { set_error("host allocation failed"); return TRX_ENOMEM; }
     ix->d = d; ix->metric = metric; ix->device = device; ix->sm_count = prop.multiProcessorCount;
+    if (getenv("TRX_NO_GRAPHS")) ix->graphs = 0;
     int kcols = d + (metric == TRX_METRIC_L2 ? 3 : 0);
     ix->Kp = (kcols + 63) / 64 * 64;
     DeviceGuard g(device);
@@ -677,6 +752,7 @@ void trx_destroy(trx_index* ix) {
 int trx_reset(trx_index* ix) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
+    ix->gen++;
     DeviceGuard g(ix->device);
     TRX_CUDA(cudaDeviceSynchronize());
     free_store(ix);
@@ -691,6 +767,7 @@ int trx_metric(const trx_index* ix) { return ix ? ix->metric : -1; }
 int trx_reserve(trx_index* ix, int64_t n) {
     if (!ix || n < 0) { set_error("bad argument"); return TRX_EINVAL; }
     DeviceGuard g(ix->device);
+    ix->gen++;
     return grow(ix, n);
 }
 
@@ -698,6 +775,7 @@ int trx_add(trx_index* ix, const float* x, int64_t n) {
     if (!ix || n < 0 || (n > 0 && !x)) { set_error("bad argument"); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
+    ix->gen++;
     DeviceGuard g(ix->device);
     TRX_TRY(grow(ix, ix->ntotal + n));
     cudaStream_t st = ix->own_stream;
@@ -720,6 +798,7 @@ int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
     if (es == 0) { set_error("add_typed: unknown dtype %d", dtype); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
+    ix->gen++;
     DeviceGuard g(ix->device);
     TRX_TRY(grow(ix, ix->ntotal + n));
     cudaStream_t st = ix->own_stream;
@@ -761,7 +840,7 @@ int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
 
 int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
-    ix->group_max = 0; ix->group_avg = 1.0;
+    ix->group_max = 0; ix->group_avg = 1.0; ix->gen++;
     if (gsrc == nullptr) { ix->has_groups = false; return TRX_OK; }
     if (n != ix->ntotal) { set_error("set_groups: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
@@ -773,6 +852,7 @@ int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
 
 int trx_set_row_attr(trx_index* ix, const int32_t* asrc, int64_t n) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    ix->gen++;
     if (asrc == nullptr) { ix->has_attr = false; ix->attr_sorted.clear(); return TRX_OK; }
     if (n != ix->ntotal) { set_error("set_row_attr: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
@@ -802,7 +882,7 @@ int trx_search_self(trx_index* ix, int64_t row0, int64_t nq, int k, const int32_
 
 int trx_set_id_offset(trx_index* ix, int64_t offset) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
-    ix->id_offset = offset;
+    ix->id_offset = offset; ix->gen++;
     return TRX_OK;
 }
 
@@ -853,6 +933,10 @@ int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t*
 
 int trx_set_option(trx_index* ix, const char* key, double v) {
     if (!ix || !key) { set_error("bad argument"); return TRX_EINVAL; }
+    {   // a cached graph stays valid when the option keeps its value (per-call modes toggle options on and off)
+        double old = 0.0;
+        if (trx_get_option(ix, key, &old) != TRX_OK || old != v) ix->gen++;
+    }
     if (!strcmp(key, "path")) {
         if (v < 0 || v > 3) { set_error("path must be 0..3"); return TRX_EINVAL; }
         ix->opt_path = (int)v;
@@ -873,6 +957,10 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->pipeline = v != 0;
     } else if (!strcmp(key, "dedup_groups")) {
         ix->dedup = v != 0;
+    } else if (!strcmp(key, "graphs")) {
+        ix->graphs = v != 0;
+    } else if (!strcmp(key, "graph_max_batch")) {
+        ix->graph_max_batch = (int)v;
     } else if (!strcmp(key, "attr_below")) {
         ix->attr_below = v >= 2147483647.0 ? INT32_MAX : (v <= -2147483648.0 ? INT32_MIN : (int32_t)v);
     } else if (!strcmp(key, "thr_bias")) {
@@ -899,6 +987,8 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "pipeline")) *v = ix->pipeline;
     else if (!strcmp(key, "attr_below")) *v = ix->attr_below;
     else if (!strcmp(key, "dedup_groups")) *v = ix->dedup;
+    else if (!strcmp(key, "graphs")) *v = ix->graphs;
+    else if (!strcmp(key, "graph_max_batch")) *v = ix->graph_max_batch;
     else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
