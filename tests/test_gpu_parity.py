@@ -535,13 +535,18 @@ def test_cuda_graph_replay_matches_plain_launches():
             D0, I0 = idx.search(xq, k, exclude=excl)
             np.testing.assert_array_equal(I1, I0); np.testing.assert_array_equal(D1, D0)
             oracle.check_parity(D1, I1, xb[:n], xq, k, IP, groups[:n] if excl is not None else None, excl)
+    # graphs were really captured and replayed (a failed capture silently falls back to plain launches)
+    assert idx.get_option("graph_captures") >= 3 and idx.get_option("graph_replays") >= 9
     idx.set_option("graphs", 1)
     idx.set_option("path", trx.PATH_UMMA)
     xq = util.gaussian(40, d, 260)
     idx.search(xq, k)
+    idx.search(xq, k)
+    c0 = idx.get_option("graph_captures")
     idx.add(xb[n:])                                        # buffers move, ntotal changes: the graph must not be reused
     D, I = idx.search(xq, k)
     oracle.check_parity(D, I, xb, xq, k, IP)
+    assert idx.get_option("graph_captures") == c0 + 1 and idx.get_option("graphs") == 1
     st = idx.stats()
     assert st["launches"] > 0
     idx.close()

@@ -145,6 +145,7 @@ struct trx_index {
     int graphs = 1;         // replay the prefilter pipeline of small batches (<= graph_max_batch) as one CUDA graph
     int graph_max_batch = 256;
     uint64_t gen = 1;       // bumped by everything that changes what a captured graph would do
+    int64_t graph_replays = 0, graph_captures = 0;
     float thr_bias = 0.f;   // experiments only: added to every estimated threshold
     BatchWs ws[2];
     // fallback-only buffers (fallbacks run synchronously, one batch at a time)
@@ -561,6 +562,7 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
                     w.graph_nodes = (int)(g_launches.load() - l0);
                     if (rc == TRX_OK && e == cudaSuccess && g != nullptr &&
                         cudaGraphInstantiate(&w.graph, g, 0) == cudaSuccess) {
+                        ix->graph_captures++;
                         w.graph_gen = ix->gen; w.graph_B = B; w.graph_k = k; w.graph_path = path;
                         w.graph_excl = w.exdev != nullptr;
                         count_launch(-w.graph_nodes);      // captured, not launched
@@ -579,6 +581,7 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
             if (w.graph != nullptr) {
                 TRX_CUDA(cudaGraphLaunch(w.graph, st));
                 count_launch(w.graph_nodes);
+                ix->graph_replays++;
                 replayed = true;
             }
         }
@@ -989,6 +992,8 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "dedup_groups")) *v = ix->dedup;
     else if (!strcmp(key, "graphs")) *v = ix->graphs;
     else if (!strcmp(key, "graph_max_batch")) *v = ix->graph_max_batch;
+    else if (!strcmp(key, "graph_replays")) *v = (double)ix->graph_replays;
+    else if (!strcmp(key, "graph_captures")) *v = (double)ix->graph_captures;
     else { set_error("unknown option '%s'", key); return TRX_EINVAL; }
     return TRX_OK;
 }
