@@ -106,3 +106,55 @@ def test_two_devices_in_one_process():
     assert torch.cuda.current_device() == 0
     np.testing.assert_array_equal(res[0][1], res[1][1])
     oracle.check_parity(res[0][0], res[0][1], xb, xq, 10, 0)
+
+
+def _fuzz_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import cpu_flat as oracle
+        from tests import util
+        from textreact_b200.sharded import ShardedIndexFlat
+        ok = 0
+        for seed in range(12):
+            rng = np.random.default_rng(4000 + seed)                 # same draws on every rank
+            d = int(rng.choice([32, 100, 256, 768]))
+            n = int(rng.choice([1001, 9000, 30001, 50000]))
+            nq = int(rng.choice([1, 5, 64, 200]))
+            k = int(rng.choice([1, 10, 100]))
+            metric = int(rng.integers(0, 2))
+            xb, xq = util.gaussian(n, d, 5000 + seed), util.gaussian(nq, d, 6000 + seed)
+            groups = (rng.permutation(n) // 3).astype(np.int32)
+            excl = groups[rng.integers(0, n, nq)].astype(np.int32) if seed % 2 else None
+            idx = ShardedIndexFlat(d, metric, device=rank, exchange="peer" if seed % 3 else "nccl")
+            idx.add_global(xb)
+            idx.set_groups_global(groups)
+            idx.local.set_option("path", int(rng.integers(0, 4)) if nq <= 8 else int(rng.choice([0, 1, 3])))
+            D, I = idx.search(xq, k, exclude=excl)                    # host arrays in / out
+            oracle.check_parity(D, I, xb, xq, k, metric, groups if excl is not None else None, excl)
+            idx.close()
+            ok += 1
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_fuzz():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_fuzz_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert dict(out) == {0: 12, 1: 12}
