@@ -114,6 +114,16 @@ int trx_set_row_attr(trx_index* idx, const int32_t* attr, int64_t n);
 int trx_search(trx_index* idx, const float* xq, int64_t nq, int k, const int32_t* excl,
                float* D, int64_t* I, void* cuda_stream);
 
+/* trx_search with per-call modes (nothing is left set on the index).  NULL params == trx_search without mask. */
+typedef struct trx_search_params_t {
+    const int32_t* exclude;  /* nullable: per-query group to exclude (-1 = none), host or device */
+    int32_t attr_below;      /* rows with attribute >= this are ineligible; 2147483647 = no filter */
+    int32_t dedup_groups;    /* 1: distinct-groups mode (see "dedup_groups" below) */
+    int64_t self_row0;       /* >= 0: the queries are the stored rows [self_row0, self_row0 + nq), xq is ignored */
+} trx_search_params_t;
+int trx_search_ex(trx_index* idx, const float* xq, int64_t nq, int k, const trx_search_params_t* params,
+                  float* D, int64_t* I, void* cuda_stream);
+
 /* trx_search with the stored rows [row0, row0+nq) as the queries -- the reference's train->train search
  * (query_fps is train_fps, retrieve/retrieve_faiss.py:114-115) without sending the corpus to the device twice. */
 int trx_search_self(trx_index* idx, int64_t row0, int64_t nq, int k, const int32_t* excl,

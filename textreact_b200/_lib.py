@@ -30,6 +30,11 @@ class TrxStats(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class TrxSearchParams(ctypes.Structure):
+    _fields_ = [("exclude", ctypes.c_void_p), ("attr_below", ctypes.c_int32), ("dedup_groups", ctypes.c_int32),
+                ("self_row0", ctypes.c_int64)]
+
+
 # every symbol include/trx.h declares, with its ctypes signature
 _vp = ctypes.c_void_p
 SIGNATURES = {
@@ -39,6 +44,7 @@ SIGNATURES = {
     "trx_reserve": (ctypes.c_int, [_vp, ctypes.c_int64]),
     "trx_set_groups": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     "trx_search": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "trx_search_ex": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(TrxSearchParams), _vp, _vp, _vp]),
     "trx_search_self": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp]),
     "trx_set_row_attr": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     "trx_reset": (ctypes.c_int, [_vp]),

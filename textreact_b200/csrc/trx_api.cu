@@ -106,7 +106,7 @@ struct BatchWs {
     // launch plan of the prefilter pipeline (prepare_prefilter) and its cached CUDA graph (small batches)
     bool pair = false; int S = 0, T = 0, r = 0, log_cap = 0;
     cudaGraphExec_t graph = nullptr; int graph_nodes = 0; uint64_t graph_gen = 0; int64_t graph_B = -1; int graph_k = 0, graph_path = 0;
-    bool graph_excl = false;
+    bool graph_excl = false; int32_t graph_attr = 0; int graph_dedup = 0;
     // the batch in flight
     int64_t B = 0; int path = 0;
     const float* qdev = nullptr; const int32_t* exdev = nullptr;
@@ -551,7 +551,8 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
                 w.exdev = w.excl;
             }
             const bool hit = w.graph != nullptr && w.graph_gen == ix->gen && w.graph_B == B && w.graph_k == k &&
-                             w.graph_path == path && w.graph_excl == (w.exdev != nullptr);
+                             w.graph_path == path && w.graph_excl == (w.exdev != nullptr) &&
+                             w.graph_attr == ix->attr_below && w.graph_dedup == ix->dedup;
             if (!hit) {
                 if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
                 cudaGraph_t g = nullptr;
@@ -565,6 +566,7 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
                         ix->graph_captures++;
                         w.graph_gen = ix->gen; w.graph_B = B; w.graph_k = k; w.graph_path = path;
                         w.graph_excl = w.exdev != nullptr;
+                        w.graph_attr = ix->attr_below; w.graph_dedup = ix->dedup;
                         count_launch(-w.graph_nodes);      // captured, not launched
                     } else {
                         w.graph = nullptr;
@@ -872,15 +874,16 @@ int trx_set_row_attr(trx_index* ix, const int32_t* asrc, int64_t n) {
     return TRX_OK;
 }
 
+static int search_impl(trx_index* ix, const float* xq, int64_t nq, int k, const trx_search_params_t* sp, float* D,
+                       int64_t* I, void* cuda_stream);
+
 int trx_search_self(trx_index* ix, int64_t row0, int64_t nq, int k, const int32_t* excl, float* D, int64_t* I,
                     void* cuda_stream) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
-    if (row0 < 0 || nq < 0 || row0 + nq > ix->ntotal) {
-        set_error("search_self: rows [%lld, %lld) outside [0, %lld)", (long long)row0, (long long)(row0 + nq), (long long)ix->ntotal);
-        return TRX_EINVAL;
-    }
-    if (nq == 0) return TRX_OK;
-    return trx_search(ix, ix->x32 + row0 * ix->d, nq, k, excl, D, I, cuda_stream);
+    if (row0 < 0) { set_error("search_self: negative row"); return TRX_EINVAL; }
+    trx_search_params_t sp;
+    sp.exclude = excl; sp.attr_below = ix->attr_below; sp.dedup_groups = ix->dedup; sp.self_row0 = row0;
+    return search_impl(ix, nullptr, nq, k, &sp, D, I, cuda_stream);
 }
 
 int trx_set_id_offset(trx_index* ix, int64_t offset) {
@@ -889,17 +892,39 @@ int trx_set_id_offset(trx_index* ix, int64_t offset) {
     return TRX_OK;
 }
 
-int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t* excl, float* D, int64_t* I,
-               void* cuda_stream) {
+// Restores the per-call modes (attr_below, dedup) that trx_search_ex overrides for the duration of one call.
+struct ModeGuard {
+    trx_index* ix; int32_t attr; int dedup;
+    explicit ModeGuard(trx_index* i) : ix(i), attr(i->attr_below), dedup(i->dedup) {}
+    ~ModeGuard() { ix->attr_below = attr; ix->dedup = dedup; }
+};
+
+static int search_impl(trx_index* ix, const float* xq, int64_t nq, int k, const trx_search_params_t* sp, float* D,
+                       int64_t* I, void* cuda_stream) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
     if (nq < 0 || k <= 0) { set_error("bad nq=%lld or k=%d", (long long)nq, k); return TRX_EINVAL; }
     if (nq == 0) return TRX_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    ModeGuard modes(ix);
+    const int32_t* excl = nullptr;
+    if (sp) {
+        excl = sp->exclude;
+        ix->attr_below = sp->attr_below;
+        ix->dedup = sp->dedup_groups != 0;
+        if (sp->self_row0 >= 0) {
+            if (sp->self_row0 + nq > ix->ntotal) {
+                set_error("search_self: rows [%lld, %lld) outside [0, %lld)", (long long)sp->self_row0,
+                          (long long)(sp->self_row0 + nq), (long long)ix->ntotal);
+                return TRX_EINVAL;
+            }
+            xq = ix->x32 + sp->self_row0 * ix->d;
+        }
+    }
     if (!xq || !D || !I) { set_error("null buffer"); return TRX_EINVAL; }
     if (k > 2048) { set_error("k=%d exceeds the supported maximum 2048", k); return TRX_EINVAL; }
     if (excl && !ix->has_groups) { set_error("exclude given but no groups set (trx_set_groups)"); return TRX_EINVAL; }
     if (ix->dedup && !ix->has_groups) { set_error("dedup_groups set but no groups set (trx_set_groups)"); return TRX_EINVAL; }
     if (ix->attr_below != INT32_MAX && !ix->has_attr) { set_error("attr_below set but no row attributes (trx_set_row_attr)"); return TRX_EINVAL; }
-    std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     const bool xq_dev = is_device_ptr(xq), out_dev = is_device_ptr(D), excl_dev = is_device_ptr(excl);
     if (out_dev != is_device_ptr(I)) { set_error("D and I must both be host or both be device pointers"); return TRX_EINVAL; }
@@ -932,6 +957,20 @@ int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t*
     }
     if (rc != TRX_OK) cudaStreamSynchronize(st);
     return rc;
+}
+
+int trx_search(trx_index* ix, const float* xq, int64_t nq, int k, const int32_t* excl, float* D, int64_t* I,
+               void* cuda_stream) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    trx_search_params_t sp;
+    sp.exclude = excl; sp.attr_below = ix->attr_below; sp.dedup_groups = ix->dedup; sp.self_row0 = -1;
+    return search_impl(ix, xq, nq, k, &sp, D, I, cuda_stream);
+}
+
+int trx_search_ex(trx_index* ix, const float* xq, int64_t nq, int k, const trx_search_params_t* params, float* D,
+                  int64_t* I, void* cuda_stream) {
+    if (!params) return trx_search(ix, xq, nq, k, nullptr, D, I, cuda_stream);
+    return search_impl(ix, xq, nq, k, params, D, I, cuda_stream);
 }
 
 int trx_set_option(trx_index* ix, const char* key, double v) {

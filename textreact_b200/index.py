@@ -20,6 +20,7 @@ dimension raises ``AssertionError`` (FAISS behaviour); engine failures raise ``R
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -28,8 +29,6 @@ from ._lib import PATH_AUTO, PATH_EXACT, PATH_STREAM, PATH_UMMA  # noqa: F401
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
-
-import os
 
 try:  # torch is plumbing only (device tensors, streams); numpy callers never need it
     if os.environ.get("TRX_NO_TORCH"):      # e.g. under compute-sanitizer: keep the process small
@@ -150,21 +149,11 @@ class IndexFlat:
             assert Dn.flags.c_contiguous and In.flags.c_contiguous
             dptr, iptr = Dn.ctypes.data, In.ctypes.data
             out = (Dn, In)
-        if attr_below is not None:
-            self.set_option("attr_below", attr_below)
-        if dedup:
-            self.set_option("dedup_groups", 1)
-        try:
-            if self_row0 is None:
-                _lib.check(self._L.trx_search(self._h, ptr, nq, int(k), ex_ptr, dptr, iptr, stream), "search")
-            else:
-                _lib.check(self._L.trx_search_self(self._h, self_row0, nq, int(k), ex_ptr, dptr, iptr, stream),
-                           "search_self")
-        finally:
-            if attr_below is not None:
-                self.set_option("attr_below", 2147483647)
-            if dedup:
-                self.set_option("dedup_groups", 0)
+        # per-call modes travel in the call (trx_search_ex): nothing is left set on the index
+        sp = _lib.TrxSearchParams(ex_ptr, 2147483647 if attr_below is None else int(attr_below), 1 if dedup else 0,
+                                  -1 if self_row0 is None else int(self_row0))
+        _lib.check(self._L.trx_search_ex(self._h, ptr, nq, int(k), ctypes.byref(sp), dptr, iptr, stream),
+                   "search" if self_row0 is None else "search_self")
         del keep, ex_keep
         return out
 
