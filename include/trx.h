@@ -129,6 +129,9 @@ int trx_search_ex(trx_index* idx, const float* xq, int64_t nq, int k, const trx_
 int trx_search_self(trx_index* idx, int64_t row0, int64_t nq, int k, const int32_t* excl,
                     float* D, int64_t* I, void* cuda_stream);
 
+/* The stored fp32 rows [row0, row0+n) -> out (host or device): FAISS's index.reconstruct / reconstruct_n. */
+int trx_reconstruct(trx_index* idx, int64_t row0, int64_t n, float* out);
+
 /* Remove all rows (keeps d / metric / options). */
 int trx_reset(trx_index* idx);
 void trx_destroy(trx_index* idx);

@@ -166,6 +166,8 @@ def test_edge_cases():
     oracle.check_parity(D, I, xb, xq[:1], 1, IP)
     with pytest.raises(AssertionError):
         idx.search(util.gaussian(2, d + 1, 64), 3)         # wrong dimension (FAISS: AssertionError)
+    np.testing.assert_array_equal(idx.reconstruct_n(0, 50), xb)          # FAISS reconstruct: the stored fp32 rows
+    np.testing.assert_array_equal(idx.reconstruct(7), xb[7])
     idx.reset()
     assert idx.ntotal == 0
     idx.close()
@@ -264,15 +266,15 @@ def test_dimensions_that_are_not_tile_multiples(metric, d):
         assert st["last_path"] == path
 
 
-@pytest.mark.parametrize("k", [1, 100, 256, 300, 1000])
+@pytest.mark.parametrize("k", [1, 100, 256, 300, 512, 1000])
 def test_k_range(k):
-    """k up to 256 stays on the prefilter path (candidate lists grow with k); beyond that the exact scan."""
+    """k up to 512 stays on the prefilter path (candidate lists grow with k); beyond that the exact scan."""
     trx = _engine()
     n, d, nq = 40000, 128, 140
     xb, xq = util.gaussian(n, d, 131), util.gaussian(nq, d, 132)
     D, I, st = _run(xb, xq, k, IP, trx.PATH_AUTO)
     oracle.check_parity(D, I, xb, xq, k, IP)
-    assert st["last_path"] == (trx.PATH_UMMA if k <= 256 else trx.PATH_EXACT)
+    assert st["last_path"] == (trx.PATH_UMMA if k <= 512 else trx.PATH_EXACT)
 
 
 def test_more_queries_than_one_batch():

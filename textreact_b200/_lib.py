@@ -47,6 +47,7 @@ SIGNATURES = {
     "trx_search_ex": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(TrxSearchParams), _vp, _vp, _vp]),
     "trx_search_self": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp]),
     "trx_set_row_attr": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
+    "trx_reconstruct": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),
     "trx_reset": (ctypes.c_int, [_vp]),
     "trx_destroy": (None, [_vp]),
     "trx_ntotal": (ctypes.c_int64, [_vp]),

@@ -245,6 +245,9 @@ static int ensure_group_stats(trx_index* ix) {
     return TRX_OK;
 }
 
+// largest k the prefilter paths serve: the candidate target is 4k and K4 keeps 4x the target in shared memory
+constexpr int kMaxPrefilterK = 512;
+
 static int candidate_cap(const trx_index* ix, int k) {
     int T = effective_target(ix, k);
     int cap = 4 * T;
@@ -517,10 +520,10 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
 
     int path = ix->opt_path;
     if (path == TRX_PATH_AUTO) {
-        if (N <= 8192 || k > 256) path = TRX_PATH_EXACT;
+        if (N <= std::max<int64_t>(8192, 2 * (int64_t)cap) || k > kMaxPrefilterK) path = TRX_PATH_EXACT;
         else if (B <= ix->stream_max_batch) path = TRX_PATH_STREAM;
         else path = TRX_PATH_UMMA;
-    } else if (path != TRX_PATH_EXACT && (N <= 2 * (int64_t)cap || k > 256)) {
+    } else if (path != TRX_PATH_EXACT && (N <= 2 * (int64_t)cap || k > kMaxPrefilterK)) {
         path = TRX_PATH_EXACT;  // prefilter needs a corpus larger than the candidate list
     }
     // a filter that keeps less than ~1/8 of the rows would starve the candidate lists: scan exactly instead
@@ -884,6 +887,16 @@ int trx_search_self(trx_index* ix, int64_t row0, int64_t nq, int k, const int32_
     trx_search_params_t sp;
     sp.exclude = excl; sp.attr_below = ix->attr_below; sp.dedup_groups = ix->dedup; sp.self_row0 = row0;
     return search_impl(ix, nullptr, nq, k, &sp, D, I, cuda_stream);
+}
+
+int trx_reconstruct(trx_index* ix, int64_t row0, int64_t n, float* out) {
+    if (!ix || !out || row0 < 0 || n < 0 || row0 + n > ix->ntotal) { set_error("reconstruct: bad rows [%lld, %lld)", (long long)row0, (long long)(row0 + n)); return TRX_EINVAL; }
+    if (n == 0) return TRX_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    TRX_CUDA(cudaMemcpy(out, ix->x32 + row0 * ix->d, (size_t)n * ix->d * 4,
+                        is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+    return TRX_OK;
 }
 
 int trx_set_id_offset(trx_index* ix, int64_t offset) {

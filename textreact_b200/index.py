@@ -160,6 +160,17 @@ class IndexFlat:
     def reset(self):
         _lib.check(self._L.trx_reset(self._h), "reset")
 
+    def reconstruct(self, key):
+        """FAISS ``index.reconstruct(i)``: the stored fp32 row."""
+        return self.reconstruct_n(int(key), 1)[0]
+
+    def reconstruct_n(self, n0=0, ni=-1):
+        """FAISS ``index.reconstruct_n(n0, ni)``: rows [n0, n0+ni) as a float32 array."""
+        ni = self.ntotal - n0 if ni < 0 else ni
+        out = np.empty((ni, self.d), dtype=np.float32)
+        _lib.check(self._L.trx_reconstruct(self._h, int(n0), int(ni), out.ctypes.data), "reconstruct")
+        return out
+
     # -- extensions -------------------------------------------------------------------------
     def reserve(self, n):
         _lib.check(self._L.trx_reserve(self._h, int(n)), "reserve")
