@@ -205,6 +205,9 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override corpus rows (debug)")
     ap.add_argument("--batch", type=int, default=0, help="override query batch (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
+                    help="N > 1 only: row-sharded corpus (north_star's contract, default) or the whole corpus on every "
+                         "GPU with the queries split (measurement beside it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -233,10 +236,19 @@ def main():
 
     rows, batch, name = workload(n_gpus, args)
     lo, hi = shard_bounds(rows, world, rank)
+    replicas = world > 1 and args.mode == "replicas"
+    if replicas:
+        lo, hi = 0, rows
+        name += " [REPLICAS mode: every GPU holds all rows, queries split]"
     stage(f"process group up; shard rows [{lo}, {hi}) batch {batch}")
 
     # ---- corpus: dist G (iid N(0,1)), generated on the device per shard, seeded ------------------
-    if world > 1:
+    ridx = None
+    if replicas:
+        from textreact_b200.sharded import ReplicatedIndexFlat
+        ridx = ReplicatedIndexFlat(D_MODEL, trx.METRIC_INNER_PRODUCT, device=local_rank)
+        sidx, local = None, ridx.local
+    elif world > 1:
         sidx = ShardedIndexFlat(D_MODEL, trx.METRIC_INNER_PRODUCT, device=local_rank)
         local = sidx.local
     else:
@@ -248,7 +260,7 @@ def main():
         if os.environ.get(env):          # tuning knobs for experiments; defaults are what is reported
             local.set_option(key, float(os.environ[env]))
     gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    gen.manual_seed(1234 + (0 if replicas else rank))
     chunk = 500_000
     first_rows = None
     for c0 in range(lo, hi, chunk):
@@ -261,7 +273,7 @@ def main():
     if sidx is not None:
         local.set_id_offset(lo)
         sidx._lo, sidx._ntotal_global = lo, rows
-    index = sidx if sidx is not None else local
+    index = ridx if ridx is not None else (sidx if sidx is not None else local)
     torch.cuda.synchronize()
     stage("corpus resident")
 
@@ -360,7 +372,7 @@ def main():
 
     # ---- multi-GPU: where the step goes -- per-rank local search time, and the exchange (all-gather + K5) alone
     multi = None
-    if world > 1:
+    if world > 1 and sidx is not None:
         mine = torch.tensor([sum(tot_ms) / len(tot_ms), sum(pre_ms) / len(pre_ms)], device=dev)
         allr = torch.empty((world, 2), device=dev)
         dist.all_gather_into_tensor(allr, mine)
@@ -384,7 +396,7 @@ def main():
                               "nccl": "NCCL all-gather of per-shard (D, I) + device k-way merge"}[mode]}
 
     kern_ms = sum(pre_ms) / len(pre_ms)
-    flops = 2.0 * batch * (hi - lo) * D_MODEL
+    flops = 2.0 * (batch / world if replicas else batch) * (hi - lo) * D_MODEL     # per rank, per K2 launch
     achieved_tf = flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
     traffic = None   # dram bytes per launch of the dominant kernel: from the committed ncu --set full capture (C2 only)
     tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
@@ -420,7 +432,7 @@ def main():
                           "dist": "iid N(0,1) fp32, seeds 1234+rank / 4321", "l2_policy": "inputs_exceed_l2 "
                           f"(bf16 corpus shard {2 * (hi - lo) * D_MODEL / 1e9:.1f} GB >> 126 MB L2)",
                           "scored_pairs_per_s": qps * rows,
-                          "exchange": None if world == 1 else f"{sidx._exchange_mode} exchange after every local search "
+                          "exchange": None if sidx is None else f"{sidx._exchange_mode} exchange after every local search "
                                       "(peer = gather fused into the merge kernel over NVLink peer memory)"},
                "clocks": clocks,
                "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": batch * D_MODEL * 4,

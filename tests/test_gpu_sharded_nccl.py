@@ -158,3 +158,44 @@ def test_two_gpu_sharded_fuzz():
         p.join(600)
         assert p.exitcode == 0
     assert dict(out) == {0: 12, 1: 12}
+
+
+def _replica_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import cpu_flat as oracle
+        from tests import util
+        from textreact_b200.sharded import ReplicatedIndexFlat
+        xb, xq = util.gaussian(30000, 128, 401), util.gaussian(301, 128, 402)       # odd query count
+        idx = ReplicatedIndexFlat(128, 0, device=rank)
+        idx.add(xb)
+        D, I = idx.search(torch.from_numpy(xq).cuda(), 10)
+        oracle.check_parity(D.cpu().numpy(), I.cpu().numpy(), xb, xq, 10, 0)
+        D2, I2 = idx.search(xq, 10)
+        np.testing.assert_array_equal(I2, I.cpu().numpy())
+        idx.close()
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_query_sharded_replicas():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = 29300 + os.getpid() % 200
+    procs = [ctx.Process(target=_replica_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert len(out) == 2

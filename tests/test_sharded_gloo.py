@@ -104,3 +104,38 @@ def test_shard_bounds_cover_rows_exactly():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _replica_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cpu_flat as oracle
+        from textreact_b200.sharded import ReplicatedIndexFlat
+        rng = np.random.default_rng(9)
+        xb = rng.standard_normal((700, 16)).astype(np.float32)
+        xq = rng.standard_normal((11, 16)).astype(np.float32)           # odd: uneven query slices
+        idx = ReplicatedIndexFlat(16, 0, local_factory=OracleLocalIndex)
+        idx.add(xb)
+        D, I = idx.search(xq, 5)
+        Do, Io = oracle.search_seq(xb, xq, 5, 0)
+        np.testing.assert_array_equal(I, Io)
+        np.testing.assert_allclose(D, Do, rtol=1e-6)
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_query_sharded_replicas():
+    world = 2
+    port = 29400 + os.getpid() % 300
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    procs = [ctx.Process(target=_replica_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert len(out) == world

@@ -47,6 +47,67 @@ class PendingSearch:
         return D, I
 
 
+class ReplicatedIndexFlat:
+    """The other way to use G GPUs when the corpus fits on one (16M x 768 is 74 GB of a B200's 180 GB): every rank
+    holds ALL rows and answers its 1/G slice of the queries; the slices are concatenated with one all-gather.
+    No merge, no per-shard rescoring redundancy -- but G copies of the corpus.  north_star's contract is the
+    row-sharded ``ShardedIndexFlat``; this is the throughput option beside it."""
+
+    def __init__(self, d, metric, *, group=None, device=None, local_factory=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.d, self.metric_type = int(d), int(metric)
+        self._on_cuda = local_factory is None          # the product path; test doubles stay on the host
+        self.local = (local_factory or (lambda d_, m_: IndexFlat(d_, m_, device=device)))(d, metric)
+
+    @property
+    def ntotal(self):
+        return self.local.ntotal
+
+    def add(self, x):
+        self.local.add(x)
+
+    def set_groups(self, groups):
+        self.local.set_groups(groups)
+
+    def search(self, xq, k, *, exclude=None, **kw):
+        """xq replicated on every rank; every rank returns the full (D, I)."""
+        nq = xq.shape[0]
+        lo, hi = shard_bounds(nq, self.world, self.rank)
+        per = -(-nq // self.world)                                  # equal slices for the all-gather (last one padded)
+        as_numpy = not (isinstance(xq, torch.Tensor) and xq.is_cuda)
+        ex = None if exclude is None else exclude[lo:hi]
+        D, I = self.local.search(xq[lo:hi].contiguous() if not as_numpy else xq[lo:hi], k, exclude=ex, **kw) \
+            if hi > lo else (None, None)
+        dev = torch.device("cuda", self.local.device) if self._on_cuda else torch.device("cpu")
+        Dp = torch.full((per, k), float("nan"), dtype=torch.float32, device=dev)
+        Ip = torch.full((per, k), -1, dtype=torch.int64, device=dev)
+        if hi > lo:
+            Dp[:hi - lo] = torch.as_tensor(D, device=dev)
+            Ip[:hi - lo] = torch.as_tensor(I, device=dev)
+        Dg = torch.empty((self.world, per, k), dtype=torch.float32, device=dev)
+        Ig = torch.empty((self.world, per, k), dtype=torch.int64, device=dev)
+        if dev.type == "cuda":
+            dist.all_gather_into_tensor(Dg, Dp, group=self.group)
+            dist.all_gather_into_tensor(Ig, Ip, group=self.group)
+        else:
+            dist.all_gather(list(Dg.unbind(0)), Dp, group=self.group)
+            dist.all_gather(list(Ig.unbind(0)), Ip, group=self.group)
+        parts_D, parts_I = [], []
+        for g in range(self.world):
+            glo, ghi = shard_bounds(nq, self.world, g)
+            parts_D.append(Dg[g, :ghi - glo]); parts_I.append(Ig[g, :ghi - glo])
+        Dm, Im = torch.cat(parts_D), torch.cat(parts_I)
+        if as_numpy:
+            return Dm.cpu().numpy(), Im.cpu().numpy()
+        return Dm, Im
+
+    def close(self):
+        if hasattr(self.local, "close"):
+            self.local.close()
+
+
 class ShardedIndexFlat:
     def __init__(self, d, metric, *, group=None, local_factory=None, merge_fn=None, device=None, exchange=None):
         self.group = group
