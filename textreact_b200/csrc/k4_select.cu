@@ -277,45 +277,44 @@ __device__ __forceinline__ float exact_score_warp(const float* __restrict__ xr, 
     return METRIC == TRX_METRIC_INNER_PRODUCT ? acc : -acc;
 }
 
-// Two rows at once: twice the gather bytes in flight per warp (the rescore is bound by the latency of ~3 KB row
-// gathers); every row keeps exactly the summation order of exact_score_warp, so scores do not depend on the pairing.
-template <int METRIC>
-__device__ __forceinline__ void exact_score_warp2(const float* __restrict__ xa, const float* __restrict__ xb,
-                                                  const float* __restrict__ sq, int d, int lane, float& ea, float& eb) {
-    float acc0 = 0.f, acc1 = 0.f;
+// RW rows at once: RW times the gather bytes in flight per warp (the rescore is bound by the latency of ~3 KB row
+// gathers); every row keeps exactly the summation order of exact_score_warp, so scores do not depend on the grouping.
+template <int METRIC, int RW>
+__device__ __forceinline__ void exact_score_warp_n(const float* const (&xr)[RW], const float* __restrict__ sq, int d,
+                                                   int lane, float (&e)[RW]) {
     if ((d & 3) == 0) {
-        const float4* a4 = reinterpret_cast<const float4*>(xa);
-        const float4* b4 = reinterpret_cast<const float4*>(xb);
+        float acc[RW];
+#pragma unroll
+        for (int r = 0; r < RW; r++) acc[r] = 0.f;
         const float4* q4 = reinterpret_cast<const float4*>(sq);
 #pragma unroll 2
         for (int c = lane; c < (d >> 2); c += 32) {
-            const float4 x = __ldg(a4 + c);
-            const float4 y = __ldg(b4 + c);
+            float4 x[RW];
+#pragma unroll
+            for (int r = 0; r < RW; r++) x[r] = __ldg(reinterpret_cast<const float4*>(xr[r]) + c);
             const float4 q = q4[c];
-            if (METRIC == TRX_METRIC_INNER_PRODUCT) {
-                acc0 = fmaf(x.x, q.x, acc0); acc0 = fmaf(x.y, q.y, acc0);
-                acc0 = fmaf(x.z, q.z, acc0); acc0 = fmaf(x.w, q.w, acc0);
-                acc1 = fmaf(y.x, q.x, acc1); acc1 = fmaf(y.y, q.y, acc1);
-                acc1 = fmaf(y.z, q.z, acc1); acc1 = fmaf(y.w, q.w, acc1);
-            } else {
-                float t0 = q.x - x.x, t1 = q.y - x.y, t2 = q.z - x.z, t3 = q.w - x.w;
-                acc0 = fmaf(t0, t0, acc0); acc0 = fmaf(t1, t1, acc0);
-                acc0 = fmaf(t2, t2, acc0); acc0 = fmaf(t3, t3, acc0);
-                float u0 = q.x - y.x, u1 = q.y - y.y, u2 = q.z - y.z, u3 = q.w - y.w;
-                acc1 = fmaf(u0, u0, acc1); acc1 = fmaf(u1, u1, acc1);
-                acc1 = fmaf(u2, u2, acc1); acc1 = fmaf(u3, u3, acc1);
+#pragma unroll
+            for (int r = 0; r < RW; r++) {
+                if (METRIC == TRX_METRIC_INNER_PRODUCT) {
+                    acc[r] = fmaf(x[r].x, q.x, acc[r]); acc[r] = fmaf(x[r].y, q.y, acc[r]);
+                    acc[r] = fmaf(x[r].z, q.z, acc[r]); acc[r] = fmaf(x[r].w, q.w, acc[r]);
+                } else {
+                    float t0 = q.x - x[r].x, t1 = q.y - x[r].y, t2 = q.z - x[r].z, t3 = q.w - x[r].w;
+                    acc[r] = fmaf(t0, t0, acc[r]); acc[r] = fmaf(t1, t1, acc[r]);
+                    acc[r] = fmaf(t2, t2, acc[r]); acc[r] = fmaf(t3, t3, acc[r]);
+                }
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+#pragma unroll
+            for (int r = 0; r < RW; r++) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
         }
-        ea = METRIC == TRX_METRIC_INNER_PRODUCT ? acc0 : -acc0;
-        eb = METRIC == TRX_METRIC_INNER_PRODUCT ? acc1 : -acc1;
+#pragma unroll
+        for (int r = 0; r < RW; r++) e[r] = METRIC == TRX_METRIC_INNER_PRODUCT ? acc[r] : -acc[r];
     } else {
-        ea = exact_score_warp<METRIC>(xa, sq, d, lane);
-        eb = exact_score_warp<METRIC>(xb, sq, d, lane);
+#pragma unroll
+        for (int r = 0; r < RW; r++) e[r] = exact_score_warp<METRIC>(xr[r], sq, d, lane);
     }
 }
 
@@ -394,14 +393,21 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(Resco
     if (m > n_valid || complete) m = n_valid;
     bool certified = false;
     for (;;) {
-        for (int i = m_done + 2 * wid; i < m; i += 2 * nwarp) {
-            const bool two = i + 1 < m;
-            const uint32_t row0 = key_id(keys[i]), row1 = two ? key_id(keys[i + 1]) : row0;
-            float e0, e1;
-            exact_score_warp2<METRIC>(a.x32 + (int64_t)row0 * a.d, a.x32 + (int64_t)row1 * a.d, sq, a.d, lane, e0, e1);
+        constexpr int RW = 3;    // rows a warp gathers at once
+        for (int i = m_done + RW * wid; i < m; i += RW * nwarp) {
+            uint32_t rows[RW];
+            const float* xr[RW];
+            float e[RW];
+#pragma unroll
+            for (int r = 0; r < RW; r++) {
+                rows[r] = key_id(keys[i + r < m ? i + r : i]);
+                xr[r] = a.x32 + (int64_t)rows[r] * a.d;
+            }
+            exact_score_warp_n<METRIC, RW>(xr, sq, a.d, lane, e);
             if (lane == 0) {
-                ekeys[i] = pack_key(e0, row0);
-                if (two) ekeys[i + 1] = pack_key(e1, row1);
+#pragma unroll
+                for (int r = 0; r < RW; r++)
+                    if (i + r < m) ekeys[i + r] = pack_key(e[r], rows[r]);
             }
         }
         const int P2 = next_pow2(m);
