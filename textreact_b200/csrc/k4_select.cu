@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(Resco
     if (m > n_valid || complete) m = n_valid;
     bool certified = false;
     for (;;) {
-        constexpr int RW = 3;    // rows a warp gathers at once
+        constexpr int RW = 3;    // rows a warp gathers at once (measured: 2 -> 710 us, 3 -> 678 us, 4 -> 690 us at C2)
         for (int i = m_done + RW * wid; i < m; i += RW * nwarp) {
             uint32_t rows[RW];
             const float* xr[RW];
