@@ -316,15 +316,18 @@ def main():
     def drain():
         pass
 
+    # nvidia-smi needs a few hundred ms before its first sample: started ahead of the warm-up steps (same load) so that
+    # the timed region is covered from its first step
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     for i in range(args.warmup):
         step_dev(i)
         drain()
         torch.cuda.synchronize()
         stage(f"warm-up step {i} done")
     launches0 = local.stats()["launches"]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ms = timed(step_dev, args.steps, drain)
     clocks = sampler.stop() if rank == 0 else None
     launches = local.stats()["launches"] - launches0
