@@ -61,7 +61,17 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.lines, self.proc = gpu_index, [], None
+        self.gpu, self.lines, self.proc, self.first, self.last = gpu_index, [], None, 0, None
+
+    def mark(self):
+        """Samples taken from now on are the ones reported (call right before the timed region)."""
+        self.first = len(self.lines)
+        self.last = None
+
+    def end(self):
+        """... up to now (call right after the timed region; one trailing sample is let in)."""
+        time.sleep(0.06)
+        self.last = len(self.lines)
 
     def start(self):
         try:
@@ -83,7 +93,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:self.last]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -328,7 +338,10 @@ def main():
         torch.cuda.synchronize()
         stage(f"warm-up step {i} done")
     launches0 = local.stats()["launches"]
+    sampler.mark()
     ms = timed(step_dev, args.steps, drain)
+    if rank == 0:
+        sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     launches = local.stats()["launches"] - launches0
     qps = batch * args.steps / (ms * 1e-3)
