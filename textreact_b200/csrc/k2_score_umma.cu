@@ -89,16 +89,35 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Blocks until the barrier phase completes.  A wait that lasts longer than kWaitTimeoutNs (a lost TMA transaction,
+// a peer CTA that died) traps: the launch fails with a CUDA error instead of hanging the GPU.
+constexpr uint64_t kWaitTimeoutNs = 20ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    const uint64_t t0 = global_timer_ns();
+    uint32_t polls = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if ((++polls & 0xfffu) == 0 && global_timer_ns() - t0 > kWaitTimeoutNs) __trap();
+    }
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

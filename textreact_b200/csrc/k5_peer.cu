@@ -81,7 +81,18 @@ __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView
     float* sD = reinterpret_cast<float*>(sI + total);
     // wait for every rank's publish of this exchange (flags live in LOCAL memory; peers store into them)
     if (threadIdx.x < G) {
-        while (ld_acquire_sys(my_flags + threadIdx.x) < want) __nanosleep(64);
+        // a peer that never publishes (crashed rank) must not hang this GPU: trap after 30 s
+        uint64_t t0 = 0;
+        uint32_t polls = 0;
+        while (ld_acquire_sys(my_flags + threadIdx.x) < want) {
+            __nanosleep(64);
+            if ((++polls & 0x3ffu) == 0) {
+                uint64_t t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 30ull * 1000 * 1000 * 1000) __trap();
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
