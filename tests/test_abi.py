@@ -61,3 +61,32 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def _compile_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "trx_example")
+    lib = os.path.join(ROOT, "textreact_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_example.c"), "-L", lib, "-ltrx",
+                           f"-Wl,-rpath,{lib}", "-o", exe])
+    return exe
+
+
+def test_header_is_plain_c_and_the_example_links(tmp_path):
+    """include/trx.h compiles as C99 with -Wall -Wextra -Werror and examples/c_abi_example.c links against libtrx.so."""
+    import subprocess
+    import torch
+    exe = _compile_example(tmp_path)
+    if not torch.cuda.is_available():
+        p = subprocess.run([exe], capture_output=True, text=True)
+        assert p.returncode == 2 and "no CPU fallback" in p.stderr          # trx_create -> TRX_ENODEV, reported not aborted
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_the_gpu(tmp_path):
+    import subprocess
+    exe = _compile_example(tmp_path)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "query 0: (0, 0.0000)" in p.stdout and "ntotal=20000" in p.stdout
