@@ -121,3 +121,36 @@ def test_c1_shape_against_an_independent_blas_topk():
     assert (same | near_tie).all()
     assert same.mean() > 0.999
     oracle.check_parity(D[:16], I[:16], xb, xq[:16], 20, 0)
+
+
+def _real_faiss():
+    try:
+        import faiss
+    except Exception:
+        return None
+    return None if str(getattr(faiss, "__version__", "")).startswith("textreact_b200") else faiss
+
+
+def test_oracle_against_real_faiss_when_it_is_installed():
+    """Pins the restatement to the real thing wherever `faiss` is importable (it is not in the build image: the
+    reference neither vendors nor pins it).  IndexFlatIP / IndexFlatL2, BLAS and scalar paths, int8 inputs."""
+    faiss = _real_faiss()
+    if faiss is None:
+        pytest.skip("faiss is not installed (un-vendored, un-pinned by the reference; no network here)")
+    from tests import util
+    xb, xq = util.gaussian(20000, 96, 31), util.gaussian(64, 96, 32)
+    for metric, cls in ((0, faiss.IndexFlatIP), (1, faiss.IndexFlatL2)):
+        for q in (xq, xq[:7]):                                # nq >= 20 -> BLAS path, < 20 -> scalar path
+            index = cls(96)
+            index.add(xb)
+            Df, If = index.search(q, 10)
+            oracle.check_parity(Df, If, xb, q, 10, metric)     # FAISS itself satisfies the north_star rule ...
+            Do, Io = oracle.search(xb, q, 10, metric)
+            assert (Io == If).mean() > 0.999                   # ... and the restatement agrees with it
+            np.testing.assert_allclose(Do, Df, rtol=2e-5, atol=2e-4)
+    fb = util.fingerprints(5000, 128, 33)
+    index = faiss.IndexFlatL2(128)
+    index.add(np.ascontiguousarray(fb, dtype="float32"))
+    Df, If = index.search(np.ascontiguousarray(fb[:30], dtype="float32"), 5)
+    Do, Io = oracle.search(fb, fb[:30], 5, 1)
+    np.testing.assert_array_equal(Do, Df)                      # integer distances: exact
