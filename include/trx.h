@@ -73,9 +73,15 @@ typedef struct trx_stats_t {
     int32_t last_path;         /* TRX_PATH_* taken by the last batch */
     int32_t sm_count;
     int64_t launches;          /* kernels of ours launched so far */
-    double last_prefilter_ms;  /* device time of the dominant scoring kernel, last batch
-                                  (only measured when option "timing" is 1) */
+    double last_prefilter_ms;  /* device time of the dominant scoring kernel, last timed batch */
     double last_total_ms;      /* device time of the whole last batch (same condition) */
+    /* Sums over every batch that carried event records (all batches except the small ones replayed as a CUDA
+     * graph): differences of two trx_stats calls give the per-stage device time of the batches in between. */
+    int64_t timed_batches;
+    double sum_sample_ms;      /* batch begin + sample pass + thresholds */
+    double sum_prefilter_ms;   /* main scoring pass (K2 tcgen05 / K3 streaming) incl. candidate scatter */
+    double sum_rescore_ms;     /* K4 exact rescore + certificate + final top-k (batches without fallbacks) */
+    double sum_total_ms;       /* whole batch up to the results being ready on the device */
 } trx_stats_t;
 
 /* Create an empty flat index of dimension d on CUDA device `device`. */

@@ -502,6 +502,65 @@ def test_distinct_groups_mode_equals_dedup_post_filter(path_name, metric):
     idx.close()
 
 
+def _dedup_reference(xb, xq, groups, k, metric, excl=None):
+    """Group leaders in (score, id) order from float64 scores: the consumer's deduplicate_neighbors on the FULL ranking."""
+    s = oracle.scores_f64(xb, xq, metric)
+    key = -s if metric == IP else s
+    out = np.full((xq.shape[0], k), -1, np.int64)
+    ids = np.arange(xb.shape[0])
+    for i in range(xq.shape[0]):
+        seen, j = set(), 0
+        for r in np.lexsort((ids, key[i])):
+            g = groups[r]
+            if g in seen or (excl is not None and g == excl[i]):
+                continue
+            seen.add(g)
+            out[i, j] = r
+            j += 1
+            if j == k:
+                break
+    return out
+
+
+@pytest.mark.parametrize("case", ["exact_small_corpus", "prefilter_fallback", "forced_exact"])
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_distinct_groups_with_groups_larger_than_the_widest_selection(case, metric):
+    """real corpora have hundreds of rows sharing one text.  k x (largest group) > 2048 used to make the
+    exact path (and through it every fallback) fail the whole call; it now scans in rounds.  One group of 1500
+    near-duplicates sits right at the top of every query, a second of 700 behind it; integer-valued data so that
+    the expected ids are exact."""
+    trx = _engine()
+    rng = np.random.default_rng(5)
+    n = 6000 if case == "exact_small_corpus" else 30000
+    d, k, nq = 64, 20, 12
+    xb = rng.integers(-3, 4, (n, d)).astype(np.float32)
+    proto = rng.integers(-3, 4, d).astype(np.float32)
+    groups = (np.arange(n) + 10).astype(np.int32)                # singletons ...
+    big = rng.choice(n, 1500, replace=False)
+    rest = np.setdiff1d(np.arange(n), big)
+    mid = rng.choice(rest, 700, replace=False)
+    xb[big] = proto; xb[big, rng.integers(0, d, 1500)] += rng.integers(-1, 2, 1500)    # ... but two large text groups
+    xb[mid] = proto; xb[mid, :2] += 1; xb[mid, rng.integers(2, d, 700)] += rng.integers(-1, 2, 700)
+    groups[big], groups[mid] = 1, 2
+    xq = (proto[None, :] + rng.integers(-1, 2, (nq, d))).astype(np.float32)
+    excl = np.full(nq, -1, np.int32); excl[::3] = 2
+    idx = trx.IndexFlat(d, metric)
+    idx.add(xb)
+    idx.set_groups(groups)
+    if case == "forced_exact":
+        idx.set_option("path", trx.PATH_EXACT)
+    elif case == "prefilter_fallback":
+        idx.set_option("path", trx.PATH_UMMA)
+    D, I = idx.search(xq, k, exclude=excl, dedup=True)
+    st = idx.stats()
+    want = _dedup_reference(xb, xq, groups, k, metric, excl)
+    np.testing.assert_array_equal(I, want)
+    assert st["queries_exact"] > 0                                # the exact scan (direct, or as the fallback) did run
+    g = groups[I]
+    assert all(len(set(row.tolist())) == k for row in g)
+    idx.close()
+
+
 def test_modes_without_their_side_data_are_errors():
     trx = _engine()
     xb = util.gaussian(2000, 32, 231)

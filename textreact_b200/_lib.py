@@ -24,6 +24,8 @@ class TrxStats(ctypes.Structure):
         ("queries_uncert", ctypes.c_int64), ("queries_overflow", ctypes.c_int64), ("rescored", ctypes.c_int64),
         ("candidates", ctypes.c_int64), ("last_path", ctypes.c_int32), ("sm_count", ctypes.c_int32),
         ("launches", ctypes.c_int64), ("last_prefilter_ms", ctypes.c_double), ("last_total_ms", ctypes.c_double),
+        ("timed_batches", ctypes.c_int64), ("sum_sample_ms", ctypes.c_double), ("sum_prefilter_ms", ctypes.c_double),
+        ("sum_rescore_ms", ctypes.c_double), ("sum_total_ms", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -131,6 +131,13 @@ struct RescoreArgs {
     uint64_t* counters;                     // [0] rescored rows [1] uncertified [2] overflow [3] candidates
 };
 int launch_rescore(const RescoreArgs& a, cudaStream_t st);
+// dynamic shared memory one K4 CTA needs; the prefilter paths are only taken when it fits kK4MaxSmem
+constexpr size_t kK4MaxSmem = 200 * 1024;
+inline size_t k4_smem_bytes(int cap, int d, int k, bool dedup) {
+    size_t smem = (size_t)cap * 16 + (size_t)((d + 3) & ~3) * 4;
+    if (dedup) smem += (size_t)cap * 4 + (size_t)k * 4 + (size_t)cap;
+    return smem;
+}
 
 // K2: tcgen05 scoring GEMM.  A = queries bf16 [nq, Kp], B = rows bf16 [n, Kp].
 struct UmmaArgs {
@@ -152,8 +159,12 @@ int umma_num_slices(int64_t n, int64_t nq, int sm_count, bool pair);  // S of th
 int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st);
 
 // Exact path, distinct-groups mode: Dx/Ix [nq, kx] sorted results (global ids) -> first k group leaders per row.
+// nfound / unfinished (nullable together): round state of the widened scan (see k4_select.cu).
 int launch_dedup_rows(const float* Dx, const int64_t* Ix, int kx, const int32_t* groups, int64_t id_offset, int k,
-                      bool l2, const int32_t* qmap, int64_t nq, float* D, int64_t* I, cudaStream_t st);
+                      bool l2, const int32_t* qmap, int64_t nq, float* D, int64_t* I, int32_t* nfound,
+                      uint32_t* unfinished, cudaStream_t st);
+int launch_mask_seen_groups(float* scores, int64_t ld, int64_t n, const int64_t* Ix, int kx, const int32_t* groups,
+                            int64_t id_offset, const int32_t* nfound, int k, int64_t nq, cudaStream_t st);
 
 // K5: merge G sorted lists per query.
 int launch_merge(int metric, const float* Dg, const int64_t* Ig, int G, int64_t nq, int k, float* D,

@@ -8,6 +8,8 @@
 #include <float.h>
 #include <limits.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace trx {
@@ -489,12 +491,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(Resco
 
 int launch_rescore(const RescoreArgs& a, cudaStream_t st) {
     if (a.nq <= 0) return TRX_OK;
-    size_t smem = (size_t)a.cap * 16 + (size_t)((a.d + 3) & ~3) * 4;
-    if (a.dedup) {
-        if (a.groups == nullptr) { set_error("k4: distinct-groups mode needs groups"); return TRX_EINVAL; }
-        smem += (size_t)a.cap * 4 + (size_t)a.k * 4 + (size_t)a.cap;
-    }
-    if (smem > 200 * 1024) { set_error("k4: cap=%d d=%d exceed shared memory", a.cap, a.d); return TRX_EINVAL; }
+    if (a.dedup && a.groups == nullptr) { set_error("k4: distinct-groups mode needs groups"); return TRX_EINVAL; }
+    const size_t smem = k4_smem_bytes(a.cap, a.d, a.k, a.dedup != 0);
+    if (smem > kK4MaxSmem) { set_error("k4: cap=%d d=%d exceed shared memory", a.cap, a.d); return TRX_EINVAL; }
     const bool wide = a.nq <= 296;   // few queries: 1024-thread CTAs so that one query's gathers use 32 warps
 #define TRX_K4(M, NT)                                                                                        \
     do {                                                                                                     \
@@ -513,25 +512,36 @@ int launch_rescore(const RescoreArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // distinct-groups filter for the exact path: rows of kx sorted results -> the first k group leaders
 // ---------------------------------------------------------------------------------------------
+// Runs in rounds when k * (largest group) exceeds the widest exact scan (kx): a round appends the leaders found in
+// its kx best rows behind the nfound[q] leaders of earlier rounds; mask_seen_groups_kernel then removes every row
+// of the groups the round saw from the score rows, so the next round's rows all belong to new groups and its
+// leaders continue the (score desc, id asc) order.  nfound[q] == k marks a finished query.
 __global__ void __launch_bounds__(128) dedup_rows_kernel(const float* __restrict__ Dx, const int64_t* __restrict__ Ix,
                                                          int kx, const int32_t* __restrict__ groups, int64_t id_offset,
                                                          int k, float fill, const int32_t* __restrict__ qmap,
-                                                         float* __restrict__ D, int64_t* __restrict__ I) {
+                                                         float* __restrict__ D, int64_t* __restrict__ I,
+                                                         int32_t* __restrict__ nfound, uint32_t* __restrict__ unfinished) {
     extern __shared__ int32_t sg[];   // [kx] group of each result (INT32_MIN for padding)
-    __shared__ int s_out;
+    __shared__ int s_out, s_valid;
     const int64_t q = blockIdx.x;
     const int64_t oq = qmap ? (int64_t)qmap[q] : q;
+    const int have = nfound ? nfound[q] : 0;
+    if (have >= k) return;            // finished in an earlier round
     const float* Dr = Dx + q * kx;
     const int64_t* Ir = Ix + q * kx;
+    if (threadIdx.x == 0) { s_out = 0; s_valid = 0; }
+    __syncthreads();
+    int nv = 0;
     for (int i = threadIdx.x; i < kx; i += blockDim.x) {
         const int64_t id = Ir[i];
         sg[i] = id >= 0 ? __ldg(groups + (id - id_offset)) : INT32_MIN;
+        nv += id >= 0 ? 1 : 0;
     }
-    if (threadIdx.x == 0) s_out = 0;
+    if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
     // leaders are taken in order by one warp: ballot over 32 results at a time keeps the order stable
     if (threadIdx.x < 32) {
-        int out = 0;
+        int out = have;
         for (int i0 = 0; i0 < kx && out < k; i0 += 32) {
             const int i = i0 + threadIdx.x;
             bool lead = false;
@@ -549,14 +559,74 @@ __global__ void __launch_bounds__(128) dedup_rows_kernel(const float* __restrict
         if (threadIdx.x == 0) s_out = out < k ? out : k;
     }
     __syncthreads();
-    for (int j = s_out + threadIdx.x; j < k; j += blockDim.x) { D[oq * k + j] = fill; I[oq * k + j] = -1; }
+    const int out = s_out;
+    // a full round list may hide further groups behind it: another round, unless k leaders are already found
+    const bool more = out < k && s_valid == kx && nfound != nullptr;
+    if (more) {
+        if (threadIdx.x == 0) { nfound[q] = out; atomicAdd(unfinished, 1u); }
+        return;
+    }
+    for (int j = out + threadIdx.x; j < k; j += blockDim.x) { D[oq * k + j] = fill; I[oq * k + j] = -1; }
+    if (threadIdx.x == 0 && nfound) nfound[q] = k;
+}
+
+// Unfinished queries: score rows of every group present in the round list Ix[q] become -inf (ineligible).
+__global__ void __launch_bounds__(256) mask_seen_groups_kernel(float* __restrict__ scores, int64_t ld, int64_t n,
+                                                               const int64_t* __restrict__ Ix, int kx,
+                                                               const int32_t* __restrict__ groups, int64_t id_offset,
+                                                               const int32_t* __restrict__ nfound, int k) {
+    extern __shared__ int32_t sgm[];  // [P] sorted groups of the round list
+    const int64_t q = blockIdx.y;
+    if (nfound[q] >= k) return;
+    int P = 2;
+    while (P < kx) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int64_t id = i < kx ? Ix[q * kx + i] : -1;
+        sgm[i] = id >= 0 ? __ldg(groups + (id - id_offset)) : INT32_MAX;
+    }
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int i = 2 * t - (t & (stride - 1)), j = i + stride;
+                const int32_t a = sgm[i], b = sgm[j];
+                if ((a > b) == ((i & size) == 0)) { sgm[i] = b; sgm[j] = a; }
+            }
+        }
+    }
+    __syncthreads();
+    float* row = scores + q * ld;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        if (!(row[r] > -INFINITY)) continue;
+        const int32_t g = __ldg(groups + r);
+        int lo = 0, hi = kx;          // an unfinished query's round list is full: the first kx sorted entries are
+        while (lo < hi) {             // exactly its groups, the padding sorts behind them
+            const int mid = (lo + hi) >> 1;
+            if (sgm[mid] < g) lo = mid + 1; else hi = mid;
+        }
+        if (lo < kx && sgm[lo] == g) row[r] = -INFINITY;
+    }
 }
 
 int launch_dedup_rows(const float* Dx, const int64_t* Ix, int kx, const int32_t* groups, int64_t id_offset, int k,
-                      bool l2, const int32_t* qmap, int64_t nq, float* D, int64_t* I, cudaStream_t st) {
+                      bool l2, const int32_t* qmap, int64_t nq, float* D, int64_t* I, int32_t* nfound,
+                      uint32_t* unfinished, cudaStream_t st) {
     if (nq <= 0) return TRX_OK;
     dedup_rows_kernel<<<(unsigned)nq, 128, (size_t)kx * 4, st>>>(Dx, Ix, kx, groups, id_offset, k, l2 ? FLT_MAX : -FLT_MAX,
-                                                                qmap, D, I);
+                                                                qmap, D, I, nfound, unfinished);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+int launch_mask_seen_groups(float* scores, int64_t ld, int64_t n, const int64_t* Ix, int kx, const int32_t* groups,
+                            int64_t id_offset, const int32_t* nfound, int k, int64_t nq, cudaStream_t st) {
+    if (nq <= 0) return TRX_OK;
+    int P = 2;
+    while (P < kx) P <<= 1;
+    const unsigned bx = (unsigned)std::min<int64_t>(296, (n + 255) / 256);
+    mask_seen_groups_kernel<<<dim3(bx, (unsigned)nq), 256, (size_t)P * 4, st>>>(scores, ld, n, Ix, kx, groups, id_offset,
+                                                                                  nfound, k);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;

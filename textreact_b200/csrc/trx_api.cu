@@ -109,6 +109,7 @@ struct BatchWs {
     bool graph_excl = false; int32_t graph_attr = 0; int graph_dedup = 0;
     // the batch in flight
     int64_t B = 0; int path = 0;
+    bool timed = false;                                    // ev[0..3] were recorded for the batch in flight
     const float* qdev = nullptr; const int32_t* exdev = nullptr;
     float* D = nullptr; int64_t* I = nullptr; bool out_dev = false, out_pinned = false;
 };
@@ -128,6 +129,7 @@ struct trx_index {
     int dedup = 0;                   // distinct-groups mode: only the best row of a group is returned
     int group_max = 0; double group_avg = 1.0;   // largest / mean group size (computed on first use)
     float* xD = nullptr; int64_t* xI = nullptr; size_t x_elems = 0;   // exact path + dedup: widened result rows
+    int32_t* x_nfound = nullptr;     // ... and the round state of scans wider than one selection
     uint32_t* norm2_max = nullptr;   // [2] float bits: max |x|^2, max |x - bf16(x)|^2 over the stored rows
     // 1/rate row sample for threshold estimation
     __nv_bfloat16* xs16 = nullptr; int64_t ns = 0, ns_cap = 0; bool sample_dirty = true;
@@ -177,7 +179,7 @@ static void free_batch_ws(BatchWs& w) {
 static void free_ws(trx_index* ix) {
     free_batch_ws(ix->ws[0]); free_batch_ws(ix->ws[1]);
     dfree(ix->fb_list2); dfree(ix->thr2); dfree(ix->neg_inf); dfree(ix->qfb); dfree(ix->exfb); dfree(ix->xscores);
-    dfree(ix->xD); dfree(ix->xI); ix->x_elems = 0;
+    dfree(ix->xD); dfree(ix->xI); dfree(ix->x_nfound); ix->x_elems = 0;
     ix->fb_batch = 0; ix->xscores_elems = 0;
 }
 
@@ -334,23 +336,23 @@ static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, 
         TRX_TRY(dmalloc(&ix->xscores, (size_t)rows * N));
         ix->xscores_elems = (size_t)rows * N;
     }
-    // distinct-groups mode: the top k * (largest group) rows always contain k group leaders
+    // distinct-groups mode: the top k * (largest group) rows always contain k group leaders.  When that exceeds the
+    // widest exact selection (2048 rows) the scan runs in rounds: leaders of the best 2048 rows, every row of the groups
+    // seen so far masked out of the score rows, next 2048 ... until k leaders are found or no row is left.
     const bool dd = dedup_active(ix);
     int kx = k;
+    bool rounds = false;
     if (dd) {
         const int64_t want = (int64_t)k * ix->group_max;
-        if (want > 2048) {
-            set_error("distinct-groups search on the exact path needs k * largest group <= 2048 (k=%d, largest group=%d)",
-                      k, ix->group_max);
-            return TRX_EINVAL;
-        }
-        kx = (int)want;
+        rounds = want > 2048;
+        kx = (int)std::min<int64_t>(want, 2048);
         if ((size_t)rows * kx > ix->x_elems) {
             dfree(ix->xD); dfree(ix->xI);
             TRX_TRY(dmalloc(&ix->xD, (size_t)rows * kx));
             TRX_TRY(dmalloc(&ix->xI, (size_t)rows * kx));
             ix->x_elems = (size_t)rows * kx;
         }
+        if (!ix->x_nfound) TRX_TRY(dmalloc(&ix->x_nfound, 1025));   // [<= 1024] leaders found so far, [1024]: unfinished count
     }
     for (int64_t q0 = 0; q0 < nq; q0 += rows) {
         int64_t nb = std::min(rows, nq - q0);
@@ -368,10 +370,22 @@ static int run_exact(trx_index* ix, const float* qdev, const int32_t* excl_dev, 
             TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, k, l2, ix->id_offset, qmap_dev ? qmap_dev + q0 : nullptr,
                                       qmap_dev ? Dd : Dd + q0 * k, qmap_dev ? Id : Id + q0 * k, st));
         } else {
-            TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, kx, l2, ix->id_offset, nullptr, ix->xD, ix->xI, st));
-            TRX_TRY(launch_dedup_rows(ix->xD, ix->xI, kx, ix->groups, ix->id_offset, k, l2,
-                                      qmap_dev ? qmap_dev + q0 : nullptr, nb, qmap_dev ? Dd : Dd + q0 * k,
-                                      qmap_dev ? Id : Id + q0 * k, st));
+            int32_t* nfound = rounds ? ix->x_nfound : nullptr;
+            uint32_t* unfinished = rounds ? reinterpret_cast<uint32_t*>(ix->x_nfound + 1024) : nullptr;
+            if (rounds) TRX_CUDA(cudaMemsetAsync(ix->x_nfound, 0, 1025 * 4, st));
+            for (;;) {
+                TRX_TRY(launch_exact_topk(ix->xscores, N, N, nb, kx, l2, ix->id_offset, nullptr, ix->xD, ix->xI, st));
+                TRX_TRY(launch_dedup_rows(ix->xD, ix->xI, kx, ix->groups, ix->id_offset, k, l2,
+                                          qmap_dev ? qmap_dev + q0 : nullptr, nb, qmap_dev ? Dd : Dd + q0 * k,
+                                          qmap_dev ? Id : Id + q0 * k, nfound, unfinished, st));
+                if (!rounds) break;
+                uint32_t left = 0;    // (the rounds path is host-synchronous: rare, and only ever on the exact path)
+                TRX_CUDA(cudaMemcpyAsync(&left, unfinished, 4, cudaMemcpyDeviceToHost, st));
+                TRX_CUDA(cudaStreamSynchronize(st));
+                if (left == 0) break;
+                TRX_CUDA(cudaMemsetAsync(unfinished, 0, 4, st));
+                TRX_TRY(launch_mask_seen_groups(ix->xscores, N, N, ix->xI, kx, ix->groups, ix->id_offset, nfound, k, nb, st));
+            }
         }
     }
     ix->st.queries_exact += nq;
@@ -465,7 +479,7 @@ static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st) 
         add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.thr, (int)B, ix->thr_bias);
         count_launch();
     }
-    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[1], st));
+    if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[1], st));
 
     if (w.path == TRX_PATH_UMMA) {
         u.x16 = ix->x16; u.n = N; u.mode = 1; u.out = nullptr;
@@ -481,7 +495,7 @@ static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st) 
         a.thr = w.thr; a.cand = w.cand; a.cand_cnt = w.cand_cnt; a.cap = w.cap;
         TRX_TRY(launch_stream(a, ix->sm_count, st));
     }
-    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[2], st));
+    if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[2], st));
 
     TRX_TRY(launch_rescore(rescore_args(ix, w, k), st));
     TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
@@ -529,9 +543,16 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
     // a filter that keeps less than ~1/8 of the rows would starve the candidate lists: scan exactly instead
     if (path != TRX_PATH_EXACT && eligible_fraction(ix) * 2048.0 < (double)std::max(ix->target, 4 * k) * 0.33)
         path = TRX_PATH_EXACT;
+    // very wide rows (d near 16384 with a large candidate list): K4's shared-memory budget would not hold
+    if (path != TRX_PATH_EXACT && k4_smem_bytes(cap, ix->d, k, dedup_active(ix)) > kK4MaxSmem) path = TRX_PATH_EXACT;
     w.path = path;
     ix->st.last_path = path;
-    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[0], st));
+    // Small batches replay a captured graph (below); every other batch carries four event records, so that the
+    // per-stage device times of the batches a caller times are available afterwards (trx_stats sums).
+    const bool graph_ok = path != TRX_PATH_EXACT && ix->graphs && B <= ix->graph_max_batch && !ix->timing &&
+                          st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    w.timed = !graph_ok;
+    if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[0], st));
 
     if (path == TRX_PATH_EXACT) {
         TRX_TRY(run_exact(ix, w.qdev, w.exdev, nullptr, B, k, w.Dd, w.Id, st));
@@ -542,8 +563,7 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
         bool replayed = false;
         // Small batches are launch-latency sensitive: the pipeline of a given (batch size, k, path) is captured once
         // and replayed as one graph.  Not on the legacy / NULL stream (not capturable) and not while timing.
-        if (ix->graphs && B <= ix->graph_max_batch && !ix->timing && st != nullptr && st != cudaStreamLegacy &&
-            st != cudaStreamPerThread) {
+        if (graph_ok) {
             // the graph reads its inputs from the workspace: bring device-resident inputs there first
             if (w.qdev != w.q32) {
                 TRX_CUDA(cudaMemcpyAsync(w.q32, w.qdev, (size_t)B * ix->d * 4, cudaMemcpyDeviceToDevice, st));
@@ -594,7 +614,7 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
     }
     // Common case (every query certified): the results leave with the same synchronisation that reads the
     // fallback count.  Otherwise finish_batch fills the missing rows and sends them again.
-    if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[3], st));
+    if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[3], st));
     TRX_TRY(send_results(ix, w, k, st));
     TRX_CUDA(cudaEventRecord(w.done, st));
     return TRX_OK;
@@ -674,7 +694,7 @@ static int finish_batch(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
             TRX_TRY(run_exact(ix, ix->qfb, exfb, ix->fb_list2, ng, k, w.Dd, w.Id, st));
             TRX_CUDA(cudaStreamSynchronize(st));   // `gen` (host) must outlive the async upload
         }
-        if (ix->timing) TRX_CUDA(cudaEventRecord(w.ev[3], st));
+        if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[3], st));
         TRX_TRY(send_results(ix, w, k, st));
         TRX_CUDA(cudaStreamSynchronize(st));
     }
@@ -682,14 +702,23 @@ static int finish_batch(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
         memcpy(w.D, w.hD, (size_t)B * k * 4);
         memcpy(w.I, w.hI, (size_t)B * k * 8);
     }
-    if (ix->timing) {
+    if (w.timed) {
         float ms = 0.f;
         TRX_CUDA(cudaEventSynchronize(w.ev[3]));
         TRX_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[3]));
         ix->st.last_total_ms = ms;
+        ix->st.sum_total_ms += ms;
+        ix->st.timed_batches++;
         if (w.path != TRX_PATH_EXACT) {
             TRX_CUDA(cudaEventElapsedTime(&ms, w.ev[1], w.ev[2]));
             ix->st.last_prefilter_ms = ms;
+            ix->st.sum_prefilter_ms += ms;
+            TRX_CUDA(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]));
+            ix->st.sum_sample_ms += ms;
+            if (nfb == 0) {   // ev[3] moves behind the fallbacks when there are any
+                TRX_CUDA(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3]));
+                ix->st.sum_rescore_ms += ms;
+            }
         } else ix->st.last_prefilter_ms = 0.0;
     }
     ix->st.queries += B;
@@ -774,6 +803,7 @@ int trx_metric(const trx_index* ix) { return ix ? ix->metric : -1; }
 
 int trx_reserve(trx_index* ix, int64_t n) {
     if (!ix || n < 0) { set_error("bad argument"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     ix->gen++;
     return grow(ix, n);
@@ -848,6 +878,7 @@ int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
 
 int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     ix->group_max = 0; ix->group_avg = 1.0; ix->gen++;
     if (gsrc == nullptr) { ix->has_groups = false; return TRX_OK; }
     if (n != ix->ntotal) { set_error("set_groups: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
@@ -860,11 +891,14 @@ int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
 
 int trx_set_row_attr(trx_index* ix, const int32_t* asrc, int64_t n) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     ix->gen++;
     if (asrc == nullptr) { ix->has_attr = false; ix->attr_sorted.clear(); return TRX_OK; }
     if (n != ix->ntotal) { set_error("set_row_attr: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
     DeviceGuard g(ix->device);
+    ix->has_attr = false;            // stays off if anything below fails
+    ix->attr_sorted.clear();
     dfree(ix->attr);
     TRX_TRY(dmalloc(&ix->attr, (size_t)n));
     const bool dev = is_device_ptr(asrc);
@@ -901,6 +935,7 @@ int trx_reconstruct(trx_index* ix, int64_t row0, int64_t n, float* out) {
 
 int trx_set_id_offset(trx_index* ix, int64_t offset) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     ix->id_offset = offset; ix->gen++;
     return TRX_OK;
 }
@@ -988,6 +1023,7 @@ int trx_search_ex(trx_index* ix, const float* xq, int64_t nq, int k, const trx_s
 
 int trx_set_option(trx_index* ix, const char* key, double v) {
     if (!ix || !key) { set_error("bad argument"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     {   // a cached graph stays valid when the option keeps its value (per-call modes toggle options on and off)
         double old = 0.0;
         if (trx_get_option(ix, key, &old) != TRX_OK || old != v) ix->gen++;
@@ -999,7 +1035,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         if (v < 1 || v > 65536) { set_error("max_batch out of range"); return TRX_EINVAL; }
         ix->max_batch = (int)v;
     } else if (!strcmp(key, "target_candidates")) {
-        if (v < 32 || v > 4096) { set_error("target_candidates out of range"); return TRX_EINVAL; }
+        // K4 keeps 4x the target (rounded up to a power of two) as 16-byte keys in shared memory: 2048 -> 8192 entries
+        if (v < 32 || v > 2048) { set_error("target_candidates out of range (32..2048)"); return TRX_EINVAL; }
         ix->target = (int)v;
     } else if (!strcmp(key, "sample_rate")) {
         if (v < 2 || v > 1024) { set_error("sample_rate out of range"); return TRX_EINVAL; }
@@ -1069,6 +1106,9 @@ int trx_merge_topk(int metric, const float* Dg, const int64_t* Ig, int G, int64_
         set_error("trx_merge_topk takes device pointers");
         return TRX_EINVAL;
     }
+    cudaPointerAttributes at;        // launch on the device that owns the lists, whatever the caller's current device is
+    TRX_CUDA(cudaPointerGetAttributes(&at, Dg));
+    DeviceGuard g(at.device);
     return launch_merge(metric, Dg, Ig, G, nq, k, D, I, (cudaStream_t)cuda_stream);
 }
 
@@ -1076,6 +1116,7 @@ int trx_debug_scores_umma(trx_index* ix, const float* xq, int64_t nq, int64_t ro
                           void* cuda_stream) {
     if (!ix || !xq || !out || nq <= 0 || n <= 0 || row0 < 0 || row0 + n > ix->ntotal) { set_error("bad argument"); return TRX_EINVAL; }
     if (!is_device_ptr(xq) || !is_device_ptr(out)) { set_error("debug_scores takes device pointers"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
     BatchWs& w = ix->ws[0];
