@@ -82,6 +82,8 @@ typedef struct trx_stats_t {
     double sum_prefilter_ms;   /* main scoring pass (K2 tcgen05 / K3 streaming) incl. candidate scatter */
     double sum_rescore_ms;     /* K4 exact rescore + certificate + final top-k (batches without fallbacks) */
     double sum_total_ms;       /* whole batch up to the results being ready on the device */
+    int64_t queries_second_pass; /* rows without a certificate answered by the batched second prefilter pass
+                                    (threshold = k-th exact score seen - eps: a complete candidate list) */
 } trx_stats_t;
 
 /* Create an empty flat index of dimension d on CUDA device `device`. */
@@ -152,7 +154,8 @@ int trx_set_id_offset(trx_index* idx, int64_t offset);
 /* Tunables: "path" (TRX_PATH_*), "max_batch", "target_candidates", "sample_rate",
  * "stream_max_batch" (crossover at or below which AUTO uses the streaming kernel),
  * "umma_pair" / "pair_min_batch" (CTA-pair tiling from this batch size on),
- * "pipeline" (0: serial batches), "attr_below" (see trx_set_row_attr; 2147483647 = off),
+ * "pipeline" (0: serial batches), "second_pass" (0: uncertified queries take an fp32 streaming sweep per 4 queries
+ * instead of one batched second tcgen05 pass), "attr_below" (see trx_set_row_attr; 2147483647 = off),
  * "dedup_groups" (1: distinct-groups mode -- of the rows that share a group (trx_set_groups) only the best
  * one is returned, so the k results are k different texts: the consumer's deduplicate_neighbors,
  * textreact/dataset.py:46-56 and :77, applied before truncation instead of after), "timing". */

@@ -93,9 +93,14 @@ def _masks(groups, exclude, nb, nq):
 
 
 def search_blas(xb, xq, k, metric=METRIC_INNER_PRODUCT, groups=None, exclude=None,
-                bs_q=4096, bs_b=1024 * 16):
-    """FAISS BLAS path (exhaustive_inner_product_blas / exhaustive_L2sqr_blas)."""
+                bs_q=4096, bs_b=1024 * 16, gemm="numpy"):
+    """FAISS BLAS path (exhaustive_inner_product_blas / exhaustive_L2sqr_blas).
+    gemm: "numpy" (the BLAS numpy links, OpenBLAS here) or "torch" (torch.mm: MKL sgemm) -- same scores up to
+    the summation order, used by bench.py's CPU arm to time the faster of the two."""
     xb, xq = coerce(xb), coerce(xq)
+    if gemm == "torch":
+        import torch
+        tb = torch.from_numpy(xb)
     nb, d = xb.shape
     nq = xq.shape[0]
     assert xq.shape[1] == d and k > 0
@@ -113,7 +118,10 @@ def search_blas(xb, xq, k, metric=METRIC_INNER_PRODUCT, groups=None, exclude=Non
         eq = None if e is None else np.ascontiguousarray(e[q0:q1])
         for b0 in range(0, nb, bs_b):
             b1 = min(nb, b0 + bs_b)
-            s = xq[q0:q1] @ xb[b0:b1].T     # fp32 sgemm
+            if gemm == "torch":
+                s = torch.mm(torch.from_numpy(xq[q0:q1]), tb[b0:b1].T).numpy()
+            else:
+                s = xq[q0:q1] @ xb[b0:b1].T     # fp32 sgemm
             if metric == METRIC_L2:
                 s = qn[q0:q1, None] + bn[None, b0:b1] - 2.0 * s
                 np.maximum(s, 0.0, out=s)

@@ -31,10 +31,22 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in L.trx_version()
 
 
-def test_stats_struct_matches_header_layout():
+def test_stats_struct_matches_header_layout(tmp_path):
+    """ctypes mirror of trx_stats_t / trx_search_params_t == what a C compiler makes of include/trx.h."""
+    import subprocess
     from textreact_b200 import _lib
-    # 7 x int64, 2 x int32, int64, 2 x double
-    assert ctypes.sizeof(_lib.TrxStats) == 7 * 8 + 2 * 4 + 8 + 2 * 8
+    fields = [n for n, _ in _lib.TrxStats._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "trx.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(trx_stats_t));\n'
+                   + "".join(f'  printf("%zu\\n", offsetof(trx_stats_t, {n}));\n' for n in fields)
+                   + '  printf("%zu\\n", sizeof(trx_search_params_t));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    assert got[0] == ctypes.sizeof(_lib.TrxStats)
+    assert got[1:-1] == [getattr(_lib.TrxStats, n).offset for n in fields]
+    assert got[-1] == ctypes.sizeof(_lib.TrxSearchParams)
 
 
 def test_no_gpu_means_error_not_fallback():

@@ -74,15 +74,21 @@ def test_prefilter_paths_gaussian(metric, path_name):
 
 
 @pytest.mark.parametrize("metric", [IP, L2])
-def test_uncertified_queries_take_exact_second_chance(metric):
+@pytest.mark.parametrize("second_pass", [1, 0])
+def test_uncertified_queries_take_exact_second_chance(metric, second_pass):
     """Starve the candidate lists so the certificate fails for many queries: they must still come back
-    exact, through the threshold-guided fp32 pass or the generic scan."""
+    exact -- through the batched second tcgen05 pass whose threshold (k-th exact score seen - eps) makes the
+    candidate list complete (default), or the threshold-guided fp32 sweep (second_pass=0), or the generic scan."""
     trx = _engine()
     n, d, nq, k = 60000, 768, 200, 20
     xb, xq = util.gaussian(n, d, 15), util.gaussian(nq, d, 16)
-    D, I, st = _run(xb, xq, k, metric, trx.PATH_UMMA, target_candidates=32)
+    D, I, st = _run(xb, xq, k, metric, trx.PATH_UMMA, target_candidates=32, second_pass=second_pass)
     oracle.check_parity(D, I, xb, xq, k, metric)
-    assert st["queries_uncert"] > 0 and st["queries_exact"] > 0, st
+    assert st["queries_uncert"] > 0, st
+    if second_pass:
+        assert st["queries_second_pass"] > 0 and st["queries_exact"] <= st["queries_uncert"] // 4, st
+    else:
+        assert st["queries_second_pass"] == 0 and st["queries_exact"] > 0, st
 
 
 def test_config1_c1_shape():
@@ -305,7 +311,7 @@ def test_pipelined_batches_match_serial_batches():
     idx.set_option("target_candidates", 64)        # starve some lists: fallbacks inside the pipeline too
     idx.set_option("pipeline", 0)
     D0, I0 = idx.search(xq, k, exclude=excl)
-    assert idx.stats()["queries_exact"] > 0
+    assert idx.stats()["queries_exact"] + idx.stats()["queries_second_pass"] > 0
     idx.set_option("pipeline", 1)
     D1, I1 = idx.search(xq, k, exclude=excl)                                    # pageable in / out
     np.testing.assert_array_equal(I1, I0); np.testing.assert_array_equal(D1, D0)
@@ -498,7 +504,7 @@ def test_distinct_groups_mode_equals_dedup_post_filter(path_name, metric):
     g = groups[I]
     assert all(len(set(row.tolist())) == k for row in g) and not (g == excl[:, None]).any()
     if path_name == "starved":
-        assert idx.stats()["queries_exact"] > 0
+        assert idx.stats()["queries_exact"] + idx.stats()["queries_second_pass"] > 0
     idx.close()
 
 

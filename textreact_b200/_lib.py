@@ -26,6 +26,7 @@ class TrxStats(ctypes.Structure):
         ("launches", ctypes.c_int64), ("last_prefilter_ms", ctypes.c_double), ("last_total_ms", ctypes.c_double),
         ("timed_batches", ctypes.c_int64), ("sum_sample_ms", ctypes.c_double), ("sum_prefilter_ms", ctypes.c_double),
         ("sum_rescore_ms", ctypes.c_double), ("sum_total_ms", ctypes.c_double),
+        ("queries_second_pass", ctypes.c_int64),
     ]
 
     def as_dict(self):

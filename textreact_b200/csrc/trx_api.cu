@@ -79,6 +79,30 @@ __global__ void add_bias_kernel(float* __restrict__ v, int n, float b) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] += b;
 }
+// Second prefilter pass of the queries without a certificate (finish_batch): query i of the pass is batch row list[i].
+// thr2[i] comes in as the k-th best EXACT score K4 saw for it (minus the fp32 summation slack) and leaves as the
+// prefilter-domain threshold  s_k (+|q|^2 for L2) - eps - eps_acc:  a row whose bf16 score is not above it cannot
+// reach s_k, so the rows above it are a complete candidate list.
+__global__ void second_pass_prep_kernel(const int32_t* __restrict__ list, int n, int Kp, int l2,
+                                        const __nv_bfloat16* __restrict__ q16, const float* __restrict__ qnorm2,
+                                        const float* __restrict__ eps, const float* __restrict__ eps_acc,
+                                        __nv_bfloat16* __restrict__ q16o, float* __restrict__ epso,
+                                        float* __restrict__ eps_acco, float* __restrict__ thr2,
+                                        uint32_t* __restrict__ cand_cnt) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const int64_t q = list[i];
+    const uint4* src = reinterpret_cast<const uint4*>(q16 + q * Kp);
+    uint4* dst = reinterpret_cast<uint4*>(q16o + (int64_t)i * Kp);
+    for (int c = threadIdx.x; c < Kp / 8; c += blockDim.x) dst[c] = src[c];
+    if (threadIdx.x == 0) {
+        const float e = eps[q], ea = eps_acc[q];
+        epso[i] = e; eps_acco[i] = ea;
+        thr2[i] = thr2[i] + (l2 ? qnorm2[q] : 0.f) - e - ea;
+        cand_cnt[i] = 0u;
+    }
+}
+
 __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ list, int n,
                                   int32_t* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,6 +168,8 @@ struct trx_index {
     int umma_pair = 1;      // allow the CTA-pair (cta_group::2) tiling
     int pair_min_batch = 129;  // ... for batches of at least this many queries (measured crossover)
     int pipeline = 1;       // overlap the upload / launch of batch i+1 with batch i when a call has several
+    int second_pass = 1;    // queries without a certificate: batched second tcgen05 pass with a threshold that makes
+                            // the candidate list complete (0: one fp32 streaming sweep per 4 queries instead)
     int graphs = 1;         // replay the prefilter pipeline of small batches (<= graph_max_batch) as one CUDA graph
     int graph_max_batch = 256;
     uint64_t gen = 1;       // bumped by everything that changes what a captured graph would do
@@ -154,6 +180,7 @@ struct trx_index {
     int fb_batch = 0;
     int32_t* fb_list2 = nullptr; float* thr2 = nullptr; float* neg_inf = nullptr;
     float* qfb = nullptr; int32_t* exfb = nullptr;
+    __nv_bfloat16* q16fb = nullptr; float* epsfb = nullptr; float* eaccfb = nullptr;   // second prefilter pass
     float* xscores = nullptr; size_t xscores_elems = 0;  // exact-path score rows
     uint64_t* counters = nullptr;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
@@ -179,6 +206,7 @@ static void free_batch_ws(BatchWs& w) {
 static void free_ws(trx_index* ix) {
     free_batch_ws(ix->ws[0]); free_batch_ws(ix->ws[1]);
     dfree(ix->fb_list2); dfree(ix->thr2); dfree(ix->neg_inf); dfree(ix->qfb); dfree(ix->exfb); dfree(ix->xscores);
+    dfree(ix->q16fb); dfree(ix->epsfb); dfree(ix->eaccfb);
     dfree(ix->xD); dfree(ix->xI); dfree(ix->x_nfound); ix->x_elems = 0;
     ix->fb_batch = 0; ix->xscores_elems = 0;
 }
@@ -298,6 +326,11 @@ static int ensure_ws(trx_index* ix, BatchWs& w, int B, int k, int cap) {
 static int ensure_fallback_ws(trx_index* ix, int B) {
     if (B <= ix->fb_batch) return TRX_OK;
     dfree(ix->fb_list2); dfree(ix->thr2); dfree(ix->neg_inf); dfree(ix->qfb); dfree(ix->exfb);
+    dfree(ix->q16fb); dfree(ix->epsfb); dfree(ix->eaccfb);
+    TRX_TRY(dmalloc(&ix->q16fb, (size_t)(B + 8) * ix->Kp));
+    TRX_CUDA(cudaMemset(ix->q16fb, 0, (size_t)(B + 8) * ix->Kp * 2));
+    TRX_TRY(dmalloc(&ix->epsfb, (size_t)B));
+    TRX_TRY(dmalloc(&ix->eaccfb, (size_t)B));
     TRX_TRY(dmalloc(&ix->fb_list2, (size_t)B));
     TRX_TRY(dmalloc(&ix->thr2, (size_t)B));
     TRX_TRY(dmalloc(&ix->neg_inf, (size_t)B));
@@ -435,6 +468,19 @@ static int send_results(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
     return TRX_OK;
 }
 
+static int ensure_hitlog(trx_index* ix, BatchWs& w, int nlogs, int log_cap) {
+    const size_t need = (size_t)nlogs * log_cap;
+    if (need > w.hitlog_elems || nlogs > w.hitlog_n) {
+        const size_t elems = std::max(need, w.hitlog_elems);
+        const int n = std::max(nlogs, w.hitlog_n);
+        dfree(w.hitlog); dfree(w.hitlog_cnt);
+        TRX_TRY(dmalloc(&w.hitlog, elems));
+        TRX_TRY(dmalloc(&w.hitlog_cnt, (size_t)n));
+        w.hitlog_elems = elems; w.hitlog_n = n; ix->gen++;
+    }
+    return TRX_OK;
+}
+
 // Sizes every buffer the prefilter pipeline of batch w needs and fixes its launch plan (no stream work here, so
 // that enqueue_prefilter can run inside a stream capture).
 static int prepare_prefilter(trx_index* ix, BatchWs& w, int k) {
@@ -450,13 +496,7 @@ static int prepare_prefilter(trx_index* ix, BatchWs& w, int k) {
         const int nlogs = grid * 128;
         double expect = 1.15 * (double)B * (double)w.T / (double)nlogs;
         w.log_cap = std::max(256, (int)(3.0 * expect) + 64);
-        size_t need_l = (size_t)nlogs * w.log_cap;
-        if (need_l > w.hitlog_elems || nlogs > w.hitlog_n) {
-            dfree(w.hitlog); dfree(w.hitlog_cnt);
-            TRX_TRY(dmalloc(&w.hitlog, need_l));
-            TRX_TRY(dmalloc(&w.hitlog_cnt, (size_t)nlogs));
-            w.hitlog_elems = need_l; w.hitlog_n = nlogs; ix->gen++;
-        }
+        TRX_TRY(ensure_hitlog(ix, w, nlogs, w.log_cap));
     }
     return TRX_OK;
 }
@@ -627,11 +667,12 @@ static int finish_batch(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
     TRX_CUDA(cudaEventSynchronize(w.done));
     const uint32_t nfb = w.path == TRX_PATH_EXACT ? 0u : *w.h_nfb;
     if (nfb > 0) {
-        // Queries without a certificate.  Second chance, still exact: K4 left the k-th best exact
-        // score it saw; every true top-k row scores at least that, so one fp32 streaming pass
-        // that appends rows above it yields a short COMPLETE list, which K4 then finishes.
-        // Only queries with no usable bound (overflow / fewer than k candidates) take the
-        // generic scan + radix select.
+        // Queries without a certificate.  Second chance, still exact: K4 left the k-th best exact score s_k it saw;
+        // every true top-k row scores at least that, hence has a bf16 score above s_k - eps.  ONE more tcgen05 pass
+        // over the bf16 corpus, batched over all such queries, with that threshold yields a COMPLETE candidate
+        // list, which K4 then finishes (its certificate holds by construction once the list is rescored).
+        // Only queries with no usable bound (overflow / fewer than k candidates) take the generic fp32 scan +
+        // radix select, 4 queries per corpus sweep.
         TRX_TRY(ensure_fallback_ws(ix, w.batch));
         std::vector<int32_t> h_list(nfb);
         std::vector<float> h_thr(nfb);
@@ -657,17 +698,37 @@ static int finish_batch(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
                 exfb = ix->exfb;
             }
             TRX_CUDA(cudaGetLastError());
-            TRX_CUDA(cudaMemsetAsync(w.cand_cnt, 0, (size_t)nl * 4, st));
             TRX_CUDA(cudaMemsetAsync(w.fb_count, 0, 4, st));
-            StreamArgs a{};
-            a.x = ix->x32; a.pitch = ix->d; a.n = N; a.d = ix->d;
-            a.q32 = ix->qfb; a.q_pitch = ix->d; a.nq = nl;
-            a.metric = ix->metric; a.bf16 = false; a.append = true;
-            a.thr = ix->thr2; a.cand = w.cand; a.cand_cnt = w.cand_cnt; a.cap = w.cap;
-            TRX_TRY(launch_stream(a, ix->sm_count, st));
             RescoreArgs rb = rescore_args(ix, w, k);
-            rb.thr = ix->neg_inf;      // complete list: certified once everything is rescored
             rb.q32 = ix->qfb; rb.nq = nl; rb.excl = exfb; rb.qmap = ix->fb_list2;
+            if (ix->second_pass) {
+                // ONE more tcgen05 pass over the bf16 corpus for all of them: threshold s_k - eps (prefilter domain)
+                second_pass_prep_kernel<<<nl, 128, 0, st>>>(ix->fb_list2, nl, ix->Kp, ix->metric == TRX_METRIC_L2, w.q16,
+                                                            w.qnorm2, w.eps, w.eps_acc, ix->q16fb, ix->epsfb, ix->eaccfb,
+                                                            ix->thr2, w.cand_cnt);
+                count_launch();
+                TRX_CUDA(cudaGetLastError());
+                UmmaArgs u{};
+                u.q16 = ix->q16fb; u.nq = nl; u.x16 = ix->x16; u.n = N; u.Kp = ix->Kp;
+                u.pair = ix->umma_pair && nl >= ix->pair_min_batch;
+                u.mode = 1; u.thr = ix->thr2; u.cand = w.cand; u.cand_cnt = w.cand_cnt; u.cap = w.cap;
+                const int nlogs = umma_grid(nl, N, ix->sm_count, u.pair, false) * 128;
+                // the band [s_k - eps, s_k] can hold several times the first pass's target: size the logs for a full list
+                const int log_cap = std::max(256, (int)(2.0 * (double)nl * (double)w.cap / (double)nlogs) + 64);
+                TRX_TRY(ensure_hitlog(ix, w, nlogs, log_cap));
+                u.log = w.hitlog; u.log_cnt = w.hitlog_cnt; u.log_cap = (int)std::min<size_t>(w.hitlog_elems / nlogs, 1u << 20);
+                TRX_TRY(launch_umma(u, ix->sm_count, st));
+                rb.thr = ix->thr2; rb.eps = ix->epsfb; rb.eps_acc = ix->eaccfb;
+            } else {
+                TRX_CUDA(cudaMemsetAsync(w.cand_cnt, 0, (size_t)nl * 4, st));
+                StreamArgs a{};
+                a.x = ix->x32; a.pitch = ix->d; a.n = N; a.d = ix->d;
+                a.q32 = ix->qfb; a.q_pitch = ix->d; a.nq = nl;
+                a.metric = ix->metric; a.bf16 = false; a.append = true;
+                a.thr = ix->thr2; a.cand = w.cand; a.cand_cnt = w.cand_cnt; a.cap = w.cap;
+                TRX_TRY(launch_stream(a, ix->sm_count, st));
+                rb.thr = ix->neg_inf;      // complete list: certified once everything is rescored
+            }
             TRX_TRY(launch_rescore(rb, st));
             TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
             TRX_CUDA(cudaStreamSynchronize(st));
@@ -677,7 +738,8 @@ static int finish_batch(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
                 gen.resize(g0 + nfb2);
                 TRX_CUDA(cudaMemcpy(gen.data() + g0, w.fb_list, (size_t)nfb2 * 4, cudaMemcpyDeviceToHost));
             }
-            ix->st.queries_exact += nl - (int64_t)nfb2;
+            if (ix->second_pass) ix->st.queries_second_pass += nl - (int64_t)nfb2;
+            else ix->st.queries_exact += nl - (int64_t)nfb2;
         }
         if (!gen.empty()) {
             const int ng = (int)gen.size();
@@ -1049,6 +1111,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->pipeline = v != 0;
     } else if (!strcmp(key, "dedup_groups")) {
         ix->dedup = v != 0;
+    } else if (!strcmp(key, "second_pass")) {
+        ix->second_pass = v != 0;
     } else if (!strcmp(key, "graphs")) {
         ix->graphs = v != 0;
     } else if (!strcmp(key, "graph_max_batch")) {
@@ -1079,6 +1143,7 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "pipeline")) *v = ix->pipeline;
     else if (!strcmp(key, "attr_below")) *v = ix->attr_below;
     else if (!strcmp(key, "dedup_groups")) *v = ix->dedup;
+    else if (!strcmp(key, "second_pass")) *v = ix->second_pass;
     else if (!strcmp(key, "graphs")) *v = ix->graphs;
     else if (!strcmp(key, "graph_max_batch")) *v = ix->graph_max_batch;
     else if (!strcmp(key, "graph_replays")) *v = (double)ix->graph_replays;
