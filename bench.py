@@ -473,11 +473,11 @@ def main():
     def settle(fn, min_steps):
         """>= min_steps untimed steps AND >= settle_s seconds of them: the first steps after an idle period run at
         boost clocks the power cap then takes away; what is timed afterwards is the sustained state."""
-        t0 = time.perf_counter()
         for i in range(min_steps):
+            t0 = time.perf_counter()
             fn(i)
             torch.cuda.synchronize()
-        per = torch.tensor([(time.perf_counter() - t0) / max(min_steps, 1)], device=dev)
+        per = torch.tensor([time.perf_counter() - t0], device=dev)       # the last one: set-up costs are behind it
         if world > 1:       # every rank must run the same number of (collective) steps: agree on the step time
             dist.all_reduce(per, op=dist.ReduceOp.MAX)
         extra = max(0, min(2000, int(settle_s / max(float(per.item()), 1e-4)) + 1 - min_steps))
@@ -615,6 +615,12 @@ def main():
         mine = torch.tensor([stages["total"], stages["prefilter"], stages["rescore"], stages["sample"]], device=dev)
         allr = torch.empty((world, 4), device=dev)
         dist.all_gather_into_tensor(allr, mine)
+        # the same steps without the exchange: what the coupling of the ranks (exchange + waiting for the slowest) costs
+        def step_local(i):
+            local.search(queries[i % len(queries)], K)
+        for i in range(3):
+            step_local(i)
+        local_only_ms = timed(step_local, args.steps) / args.steps
         Dl, Il = local.search(queries[0], K)
 
         def exchange(i):
@@ -631,6 +637,7 @@ def main():
                  "k2_ms_per_rank": [round(float(v), 3) for v in allr[:, 1].tolist()],
                  "k4_ms_per_rank": [round(float(v), 3) for v in allr[:, 2].tolist()],
                  "sample_pass_ms_per_rank": [round(float(v), 3) for v in allr[:, 3].tolist()],
+                 "local_only_ms_per_step": local_only_ms,
                  "exchange_mode": mode, "exchange_ms": ex_ms[mode], "exchange_ms_by_mode": ex_ms,
                  "exchange": {"peer": "ONE kernel: all-gather fused into the k-way merge over NVLink peer memory "
                                       "(CUDA IPC export buffers, flag protocol, no NCCL in the data path)",

@@ -53,6 +53,25 @@ __host__ __device__ __forceinline__ float key_score(uint64_t k) { return key2f(~
 __host__ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return (uint32_t)k; }
 static constexpr uint64_t KEY_SENTINEL = 0xffffffffffffffffull;  // sorts last
 
+#ifdef __CUDACC__
+// In-place ascending bitonic sort of P (power of two) 64-bit keys in shared memory, by the whole CTA.
+__device__ __forceinline__ void bitonic_sort_u64(uint64_t* keys, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                uint64_t a = keys[i], b = keys[j];
+                bool up = (i & size) == 0;
+                if ((a > b) == up) { keys[i] = b; keys[j] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+#endif
+
 // A prefilter candidate: bf16-pipeline score + local row.
 struct __align__(8) Cand {
     float score;

@@ -51,22 +51,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-__device__ __forceinline__ void bitonic_sort_keys(uint64_t* keys, int P) {
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-                int i = 2 * t - (t & (stride - 1));
-                int j = i + stride;
-                uint64_t a = keys[i], b = keys[j];
-                bool up = (i & size) == 0;
-                if ((a > b) == up) { keys[i] = b; keys[j] = a; }
-            }
-        }
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView pv, const unsigned long long* my_flags,
                                                             unsigned long long want, int G, int64_t nq, int k,
                                                             float* __restrict__ D, int64_t* __restrict__ I) {
@@ -107,7 +91,7 @@ __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView
         }
         keys[i] = key;
     }
-    bitonic_sort_keys(keys, P);
+    bitonic_sort_u64(keys, P);
     const float fill = metric == TRX_METRIC_L2 ? FLT_MAX : -FLT_MAX;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         const uint64_t key = keys[j];
