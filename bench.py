@@ -186,7 +186,7 @@ def cpu_flat_search_timed(xb, xq, k, steps, warmup):
 
 def run_reference(args):
     """--impl reference: the reference's CPU flat search (real faiss when importable; else the oracle restatement --
-    faiss is un-vendored, un-pinned and unobtainable offline, profiles/r2a_try_faiss_on_gpu_box.log) on the box's host
+    faiss is un-vendored, un-pinned and unobtainable offline, profiles/round2_a_try_faiss_on_gpu_box.log) on the box's host
     cores, on the FULL corpus of the configuration.  A step is a bounded sample of one batch's QUERIES (1,024 of 4,096
     at N = 1; scaled down with the corpus size at N > 1 so a step stays ~6 s); nothing is extrapolated in rows, and
     ms_per_step is the measured time of what was run."""
