@@ -374,6 +374,10 @@ def main():
                     help="comma list of the extra N=1 legs: c5,c3,dists,strong_base,cpu (default: all; 'none')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-queries", type=int, default=0, help="--impl reference: queries per step (default: bounded)")
+    ap.add_argument("--merge", default="slice", choices=["slice", "full"],
+                    help="N > 1: 'slice' = the merge is sharded too, rank g ends up with the merged top-k of queries "
+                         "[g*B/N, (g+1)*B/N) (1/N of the exchange traffic; every answer exists on one rank); 'full' = every "
+                         "rank ends up with every query's result")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1 only: row-sharded corpus (north_star's contract, default) or the whole corpus on every "
                          "GPU with the queries split (measurement beside it)")
@@ -516,8 +520,10 @@ def main():
         sampler.start()
         time.sleep(0.3)
 
+    merge_kw = {"result": args.merge} if sidx is not None else {}
+
     def step_dev(i):
-        index.search(queries[i % len(queries)], K)
+        index.search(queries[i % len(queries)], K, **merge_kw)
     n_settle = settle(step_dev, args.warmup)
     stage(f"{n_settle} warm-up / settle steps done")
     s0 = local.stats()
@@ -548,8 +554,9 @@ def main():
 
         def step_e2e(i):
             dq.copy_(hq[i % 2], non_blocking=True)           # H2D of the replicated query batch
-            Dm, Im = index.search(dq, K)
-            hD.copy_(Dm, non_blocking=True); hI.copy_(Im, non_blocking=True)   # D2H of the merged result
+            Dm, Im = index.search(dq, K, **merge_kw)
+            n_out = Dm.shape[0]                               # D2H of the merged result (this rank's slice of it)
+            hD[:n_out].copy_(Dm, non_blocking=True); hI[:n_out].copy_(Im, non_blocking=True)
             torch.cuda.current_stream().synchronize()
     settle(step_e2e, 2)
     barrier()
@@ -562,7 +569,8 @@ def main():
     # ---- parity of what was just timed: 32 queries against a float64 top-k over the same rows -----------------
     def parity(idx_search, d_name, r_lo, r_hi, r_total, qbuf, modes=("default",)):
         kk = K + PARITY_EXTRA
-        xq = qbuf[:PARITY_Q]
+        pq = torch.arange(PARITY_Q, device=dev) * (qbuf.shape[0] // PARITY_Q)     # spread over the batch (and the slices)
+        xq = qbuf[pq].contiguous()
         D64, I64, N64 = fp64_topk_local(d_name, r_lo, r_hi, r_total, dev, seed, xq, kk)
         if world > 1 and not replicas:
             gD = torch.empty((world,) + tuple(D64.shape), dtype=D64.dtype, device=dev)
@@ -581,8 +589,17 @@ def main():
         ok = True
         for m in modes:
             D, I = idx_search(qbuf, m)
-            r = north_star_rule(D[:PARITY_Q].cpu().numpy(), I[:PARITY_Q].cpu().numpy(), D64.cpu().numpy(),
-                                I64.cpu().numpy(), N64.cpu().numpy(), qn, K)
+            rows = pq
+            sel = torch.ones(PARITY_Q, dtype=torch.bool, device=dev)
+            if m.endswith("_slice"):       # this rank holds the merged rows [q_lo, q_hi) only
+                q_lo, q_hi = sidx.query_slice(qbuf.shape[0])
+                sel = (pq >= q_lo) & (pq < q_hi)
+                rows = pq[sel] - q_lo
+            sel_c = sel.cpu().numpy()
+            r = north_star_rule(D[rows].cpu().numpy(), I[rows].cpu().numpy(), D64.cpu().numpy()[sel_c],
+                                I64.cpu().numpy()[sel_c], N64.cpu().numpy()[sel_c], qn[sel_c], K)
+            if m.endswith("_slice"):
+                r["queries_on_this_rank"] = int(sel.sum().item())
             ok = ok and r["ok"]
             if len(modes) == 1:
                 out.update(r)
@@ -598,12 +615,13 @@ def main():
     if sidx is not None:
         def search_mode(qbuf, m):
             keep = sidx._exchange_mode
-            sidx._exchange_mode = m
+            sidx._exchange_mode = m.replace("_slice", "")
             try:
-                return sidx.search(qbuf, K)
+                return sidx.search(qbuf, K, result="slice" if m.endswith("_slice") else "full")
             finally:
                 sidx._exchange_mode = keep
         modes = [sidx._exchange_mode] + (["nccl"] if sidx._exchange_mode == "peer" else [])
+        modes += [sidx._exchange_mode + "_slice"]
         parity_checked = parity(search_mode, args.dist, lo, hi, rows, queries[0], tuple(modes))
     else:
         parity_checked = parity(lambda qbuf, m: index.search(qbuf, K), args.dist, lo, hi, rows, queries[0])
@@ -623,22 +641,26 @@ def main():
         local_only_ms = timed(step_local, args.steps) / args.steps
         Dl, Il = local.search(queries[0], K)
 
-        def exchange(i):
-            sidx.exchange(Dl, Il)
         mode = sidx._exchange_mode
         ex_ms = {}
-        for m in ([mode, "nccl"] if mode == "peer" else [mode]):      # the mode in use, and NCCL beside it
-            sidx._exchange_mode = m
+        for m in ([mode + "_slice", mode, "nccl"] if mode == "peer" else [mode + "_slice", mode]):   # in use, and beside it
+            sidx._exchange_mode = m.replace("_slice", "")
+
+            def exchange(i, res="slice" if m.endswith("_slice") else "full"):
+                sidx.exchange(Dl, Il, result=res)
             for i in range(3):
                 exchange(i)
             ex_ms[m] = timed(exchange, 10) / 10
         sidx._exchange_mode = mode
+        mode_used = mode + ("_slice" if args.merge == "slice" else "")
         multi = {"local_ms_per_rank": [round(float(v), 3) for v in allr[:, 0].tolist()],
                  "k2_ms_per_rank": [round(float(v), 3) for v in allr[:, 1].tolist()],
                  "k4_ms_per_rank": [round(float(v), 3) for v in allr[:, 2].tolist()],
                  "sample_pass_ms_per_rank": [round(float(v), 3) for v in allr[:, 3].tolist()],
                  "local_only_ms_per_step": local_only_ms,
-                 "exchange_mode": mode, "exchange_ms": ex_ms[mode], "exchange_ms_by_mode": ex_ms,
+                 "exchange_mode": mode_used, "exchange_ms": ex_ms[mode_used], "exchange_ms_by_mode": ex_ms,
+                 "merge": {"slice": "the merge is sharded: rank g merges (and keeps) queries [g*B/N, (g+1)*B/N)",
+                           "full": "every rank merges every query"}[args.merge],
                  "exchange": {"peer": "ONE kernel: all-gather fused into the k-way merge over NVLink peer memory "
                                       "(CUDA IPC export buffers, flag protocol, no NCCL in the data path)",
                               "nccl": "NCCL all-gather of per-shard (D, I) + device k-way merge"}[mode]}
@@ -678,10 +700,12 @@ def main():
                                       "origin is the strong_base leg of the N = 1 line (value at N = 1 is C2, the "
                                       "configuration the metric is quoted on)",
                       "exchange": None if sidx is None else f"{sidx._exchange_mode} exchange after every local search "
-                                  "(peer = gather fused into the merge kernel over NVLink peer memory)"},
+                                  f"(peer = gather fused into the merge kernel over NVLink peer memory), merge = {args.merge}"},
            "clocks": clocks,
            "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": batch * D_MODEL * 4,
                    "d2h_bytes_per_step": batch * K * 12, "ms_per_step": ms_e2e_dev / args.steps,
+                   "d2h_note": None if sidx is None else ("summed over ranks: each rank reads back its slice" if args.merge == "slice"
+                                                         else "per rank: every rank reads back the full result"),
                    "wall_ms_per_step": wall_e2e * 1e3 / args.steps},
            "gpu_launches": int(launches),
            "roofline": roofline,

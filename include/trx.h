@@ -183,6 +183,11 @@ int trx_exchange_handle(trx_exchange* ex, unsigned char* handle64);
 int trx_exchange_connect(trx_exchange* ex, const unsigned char* handles);
 int trx_exchange_merge(trx_exchange* ex, int metric, const float* D_local, const int64_t* I_local, int64_t nq, int k,
                        float* D, int64_t* I, void* cuda_stream);
+/* The same exchange with the merge itself sharded: this rank receives the merged top-k of queries [q0, q0 + nq_out)
+ * only (D, I: [nq_out, k]) and loads 1/world of the peers' entries.  Every rank still passes all nq local lists, and
+ * every rank must take part in every exchange (nq_out may be 0). */
+int trx_exchange_merge_slice(trx_exchange* ex, int metric, const float* D_local, const int64_t* I_local, int64_t nq, int k,
+                             int64_t q0, int64_t nq_out, float* D, int64_t* I, void* cuda_stream);
 void trx_exchange_destroy(trx_exchange* ex);
 
 /* Raw bf16 scoring GEMM on the tcgen05 path, for tests and profiling:

@@ -42,6 +42,13 @@ def _worker(rank, world, port, metric, with_mask, exchange, out):
         # host arrays in -> host arrays out
         D2, I2 = idx.search(xq[:33], k, exclude=None if excl is None else excl[:33])
         np.testing.assert_array_equal(I2, I.cpu().numpy()[:33])
+        # sharded merge: each rank receives only its slice of the queries (1/world of the exchange traffic)
+        Ds, Is = idx.search(torch.from_numpy(xq).cuda(), k, exclude=None if excl is None else torch.from_numpy(excl).cuda(),
+                            result="slice")
+        qlo, qhi = idx.query_slice(nq)
+        assert tuple(Is.shape) == (qhi - qlo, k)
+        np.testing.assert_array_equal(Is.cpu().numpy(), I.cpu().numpy()[qlo:qhi])
+        np.testing.assert_array_equal(Ds.cpu().numpy(), D.cpu().numpy()[qlo:qhi])
         # pipelined form: several exchanges pending while later local searches run
         xq_t = torch.from_numpy(xq).cuda()
         ex_t = None if excl is None else torch.from_numpy(excl).cuda()

@@ -75,6 +75,12 @@ def _worker(rank, world, port, metric, with_mask, out):
         Do, Io = oracle.search_seq(xb, xq, k, metric, groups if with_mask else None, excl)
         np.testing.assert_array_equal(I, Io)
         np.testing.assert_allclose(D, Do, rtol=1e-6)
+        # sharded merge: this rank keeps the merged rows of its query slice only
+        Ds, Is = idx.search(xq, k, exclude=excl, result="slice")
+        qlo, qhi = idx.query_slice(nq)
+        assert (qlo, qhi) == shard_bounds(nq, world, rank) and Is.shape == (qhi - qlo, k)
+        np.testing.assert_array_equal(Is, Io[qlo:qhi])
+        np.testing.assert_allclose(Ds, Do[qlo:qhi], rtol=1e-6)
         out[rank] = True
     finally:
         dist.destroy_process_group()

@@ -65,6 +65,8 @@ SIGNATURES = {
     "trx_exchange_handle": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "trx_exchange_connect": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "trx_exchange_merge": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
+    "trx_exchange_merge_slice": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
+                                                ctypes.c_int64, _vp, _vp, _vp]),
     "trx_exchange_destroy": (None, [_vp]),
     "trx_debug_scores_umma": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _vp, _vp]),
     "trx_last_error": (ctypes.c_char_p, []),

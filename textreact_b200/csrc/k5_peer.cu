@@ -52,10 +52,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView pv, const unsigned long long* my_flags,
-                                                            unsigned long long want, int G, int64_t nq, int k,
+                                                            unsigned long long want, int G, int64_t q0, int k,
                                                             float* __restrict__ D, int64_t* __restrict__ I) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int64_t q = blockIdx.x;
+    const int64_t q = q0 + blockIdx.x;      // query of the exchanged lists; output row blockIdx.x (a slice starts at q0)
+    const int64_t oq = blockIdx.x;
     const int total = G * k;
     int P = 2;
     while (P < total) P <<= 1;
@@ -95,11 +96,11 @@ __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView
     const float fill = metric == TRX_METRIC_L2 ? FLT_MAX : -FLT_MAX;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         const uint64_t key = keys[j];
-        if (key == KEY_SENTINEL) { D[q * k + j] = fill; I[q * k + j] = -1; }
+        if (key == KEY_SENTINEL) { D[oq * k + j] = fill; I[oq * k + j] = -1; }
         else {
             const int pos = (int)key_id(key);
-            D[q * k + j] = sD[pos];
-            I[q * k + j] = sI[pos];
+            D[oq * k + j] = sD[pos];
+            I[oq * k + j] = sI[pos];
         }
     }
 }
@@ -192,7 +193,13 @@ int trx_exchange_connect(trx_exchange* ex, const unsigned char* handles) {
 
 int trx_exchange_merge(trx_exchange* ex, int metric, const float* D_local, const int64_t* I_local, int64_t nq, int k,
                        float* D, int64_t* I, void* cuda_stream) {
-    if (!ex || !D_local || !I_local || !D || !I || nq <= 0 || k <= 0) { set_error("bad argument"); return TRX_EINVAL; }
+    return trx_exchange_merge_slice(ex, metric, D_local, I_local, nq, k, 0, nq, D, I, cuda_stream);
+}
+
+int trx_exchange_merge_slice(trx_exchange* ex, int metric, const float* D_local, const int64_t* I_local, int64_t nq, int k,
+                             int64_t q0, int64_t nq_out, float* D, int64_t* I, void* cuda_stream) {
+    if (!ex || !D_local || !I_local || nq <= 0 || k <= 0 || q0 < 0 || nq_out < 0 || q0 + nq_out > nq ||
+        (nq_out > 0 && (!D || !I))) { set_error("bad argument"); return TRX_EINVAL; }
     if (!ex->connected && ex->world > 1) { set_error("exchange: not connected"); return TRX_EINVAL; }
     if (nq * k > ex->max_entries) { set_error("exchange: %lld entries exceed the export buffer (%lld)", (long long)(nq * k), (long long)ex->max_entries); return TRX_EINVAL; }
     ExDeviceGuard g(ex->device);
@@ -217,9 +224,11 @@ int trx_exchange_merge(trx_exchange* ex, int metric, const float* D_local, const
     const size_t smem = (size_t)P * 8 + (size_t)total * 12;
     if (smem > 200 * 1024) { set_error("exchange: world*k=%lld too large", (long long)total); return TRX_EINVAL; }
     TRX_CUDA(cudaFuncSetAttribute(k5_peer_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k5_peer_merge_kernel<<<(unsigned)nq, 256, smem, st>>>(metric, pv, reinterpret_cast<const unsigned long long*>(ex->base),
-                                                          want, ex->world, nq, k, D, I);
-    count_launch();
+    if (nq_out > 0) {     // (a rank with an empty slice still publishes its lists)
+        k5_peer_merge_kernel<<<(unsigned)nq_out, 256, smem, st>>>(metric, pv, reinterpret_cast<const unsigned long long*>(ex->base),
+                                                                  want, ex->world, q0, k, D, I);
+        count_launch();
+    }
     TRX_CUDA(cudaGetLastError());
     ex->step++;
     return TRX_OK;

@@ -151,11 +151,17 @@ class ShardedIndexFlat:
         lo, hi = self._lo, self._lo + self.local.ntotal
         self.local.set_row_attr(attr[lo:hi])
 
-    def search(self, xq, k, *, exclude=None, attr_below=None):
-        """xq replicated on every rank.  Returns (D, I) on every rank (numpy in -> numpy out)."""
-        return self.search_async(xq, k, exclude=exclude, attr_below=attr_below).result()
+    def query_slice(self, nq):
+        """Rows [lo, hi) of an nq-query batch whose merged result this rank holds under ``result="slice"``."""
+        return shard_bounds(nq, self.world, self.rank)
 
-    def search_async(self, xq, k, *, exclude=None, attr_below=None):
+    def search(self, xq, k, *, exclude=None, attr_below=None, result="full"):
+        """xq replicated on every rank.  ``result="full"``: (D, I) of every query on every rank (numpy in -> numpy
+        out).  ``result="slice"``: the merge itself is sharded -- this rank gets the merged top-k of the queries
+        ``query_slice(nq)`` only ([hi - lo, k]); 1/world of the exchange traffic, every answer exists on one rank."""
+        return self.search_async(xq, k, exclude=exclude, attr_below=attr_below, result=result).result()
+
+    def search_async(self, xq, k, *, exclude=None, attr_below=None, result="full"):
         """Local search now, exchange (all-gather + merge) queued on a side stream: the returned handle's
         ``result()`` orders the caller's stream after it.  Calling ``search_async`` for batch i+1 before
         ``result()`` of batch i lets the exchange of batch i -- and the wait for the slowest rank that comes
@@ -179,15 +185,16 @@ class ShardedIndexFlat:
         D, I = self.local.search(xq, k, exclude=exclude, **kw)       # complete on return (host-synchronised)
         if not isinstance(D, torch.Tensor):
             D, I = torch.from_numpy(D), torch.from_numpy(I)
+        assert result in ("full", "slice")
         if not D.is_cuda:                                              # CPU test doubles: nothing to overlap
-            Dm, Im = self.exchange(D, I)
+            Dm, Im = self.exchange(D, I, result=result)
             return PendingSearch(Dm, Im, None, as_numpy)
         if self._xstream is None:
             self._xstream = torch.cuda.Stream(device=D.device)
         cur = torch.cuda.current_stream(D.device)
         self._xstream.wait_stream(cur)
         with torch.cuda.stream(self._xstream):
-            Dm, Im = self.exchange(D, I)
+            Dm, Im = self.exchange(D, I, result=result)
             ev = torch.cuda.Event()
             ev.record(self._xstream)
         for t in (D, I):
@@ -225,18 +232,22 @@ class ShardedIndexFlat:
         self._peer, self._peer_entries = ex, entries
         return ex
 
-    def exchange(self, D, I):
-        """The one exchange step: the per-shard [nq, k] lists of every rank -> the merged top-k on every rank.
+    def exchange(self, D, I, result="full"):
+        """The one exchange step: the per-shard [nq, k] lists of every rank -> the merged top-k, on every rank
+        (``result="full"``) or each rank its ``query_slice`` of it (``"slice"``).
         CUDA default: ONE kernel that gathers over NVLink peer memory and merges (K5p, k5_peer.cu);
         otherwise all-gather (NCCL / gloo) + k-way merge (K5)."""
+        q_lo, q_hi = (0, D.shape[0]) if result == "full" else self.query_slice(D.shape[0])
         if D.is_cuda and self._exchange_mode == "peer" and self.world > 1:
             ex = self._peer_exchange(D.shape[0], D.shape[1], D.device)
             if ex is not None:
                 D, I = D.contiguous(), I.contiguous()
-                Dm, Im = torch.empty_like(D), torch.empty_like(I)
-                _lib.check(_lib.lib().trx_exchange_merge(ex, self.metric_type, D.data_ptr(), I.data_ptr(), D.shape[0],
-                                                         D.shape[1], Dm.data_ptr(), Im.data_ptr(),
-                                                         _stream_handle(D.device)), "exchange_merge")
+                Dm = torch.empty((q_hi - q_lo, D.shape[1]), dtype=D.dtype, device=D.device)
+                Im = torch.empty((q_hi - q_lo, I.shape[1]), dtype=I.dtype, device=I.device)
+                _lib.check(_lib.lib().trx_exchange_merge_slice(ex, self.metric_type, D.data_ptr(), I.data_ptr(),
+                                                               D.shape[0], D.shape[1], q_lo, q_hi - q_lo,
+                                                               Dm.data_ptr(), Im.data_ptr(),
+                                                               _stream_handle(D.device)), "exchange_merge")
                 return Dm, Im
         Dg = torch.empty((self.world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
         Ig = torch.empty((self.world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
@@ -246,7 +257,8 @@ class ShardedIndexFlat:
         else:             # gloo (CPU tests of the host logic): list-of-views form
             dist.all_gather(list(Dg.unbind(0)), D.contiguous(), group=self.group)
             dist.all_gather(list(Ig.unbind(0)), I.contiguous(), group=self.group)
-        return self._merge(Dg, Ig, self.metric_type)
+        # (the all-gather moves every list either way: a slice is the merged rows this rank keeps)
+        return self._merge(Dg[:, q_lo:q_hi].contiguous(), Ig[:, q_lo:q_hi].contiguous(), self.metric_type)
 
     def close(self):
         if self._peer is not None:
