@@ -378,6 +378,8 @@ def main():
                     help="N > 1: 'slice' = the merge is sharded too, rank g ends up with the merged top-k of queries "
                          "[g*B/N, (g+1)*B/N) (1/N of the exchange traffic; every answer exists on one rank); 'full' = every "
                          "rank ends up with every query's result")
+    ap.add_argument("--shards", default="calibrated", choices=["calibrated", "even"],
+                    help="N > 1: shard sizes proportional to each GPU's measured scoring speed (default), or equal")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1 only: row-sharded corpus (north_star's contract, default) or the whole corpus on every "
                          "GPU with the queries split (measurement beside it)")
@@ -415,13 +417,7 @@ def main():
     settle_s = float(os.environ.get("TRX_BENCH_SETTLE_S", "1.0"))
 
     rows, batch, name = workload(n_gpus, args)
-    lo, hi = shard_bounds(rows, world, rank)
     replicas = world > 1 and args.mode == "replicas"
-    if replicas:
-        lo, hi = 0, rows
-        name += " [REPLICAS mode: every GPU holds all rows, queries split]"
-    stage(f"process group up; shard rows [{lo}, {hi}) batch {batch}")
-
     ridx = None
     if replicas:
         from textreact_b200.sharded import ReplicatedIndexFlat
@@ -433,6 +429,17 @@ def main():
     else:
         sidx = None
         local = trx.IndexFlatIP(D_MODEL, device=local_rank)
+    # Shards: B200s under the 1 kW cap differ by several per cent in sustained tensor throughput and every step waits
+    # for the slowest rank, so each rank first measures its scoring speed on a throw-away index (1.5 s) and the rows are
+    # split in proportion (ShardedIndexFlat.calibrate); --shards even gives the plain N/G split.
+    weights = None
+    if sidx is not None and args.shards == "calibrated":
+        weights = sidx.calibrate(batch=batch)
+    lo, hi = shard_bounds(rows, world, rank, weights)
+    if replicas:
+        lo, hi = 0, rows
+        name += " [REPLICAS mode: every GPU holds all rows, queries split]"
+    stage(f"process group up; shard rows [{lo}, {hi}) batch {batch}" + (f"; speed weights {[round(w, 4) for w in weights]}" if weights else ""))
     want_base = "strong_base" in legs
     local.reserve(16_000_000 if want_base else hi - lo)
     for key, env in (("target_candidates", "TRX_TARGET"), ("sample_rate", "TRX_SAMPLE_RATE"), ("path", "TRX_PATH"), ("thr_bias", "TRX_THR_BIAS"),
@@ -653,7 +660,10 @@ def main():
             ex_ms[m] = timed(exchange, 10) / 10
         sidx._exchange_mode = mode
         mode_used = mode + ("_slice" if args.merge == "slice" else "")
-        multi = {"local_ms_per_rank": [round(float(v), 3) for v in allr[:, 0].tolist()],
+        multi = {"shards": {"policy": args.shards, "speed_weights": weights,
+                            "rows_per_rank": [shard_bounds(rows, world, r, weights)[1] - shard_bounds(rows, world, r, weights)[0]
+                                              for r in range(world)]},
+                 "local_ms_per_rank": [round(float(v), 3) for v in allr[:, 0].tolist()],
                  "k2_ms_per_rank": [round(float(v), 3) for v in allr[:, 1].tolist()],
                  "k4_ms_per_rank": [round(float(v), 3) for v in allr[:, 2].tolist()],
                  "sample_pass_ms_per_rank": [round(float(v), 3) for v in allr[:, 3].tolist()],

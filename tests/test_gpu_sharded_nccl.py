@@ -28,8 +28,13 @@ def _worker(rank, world, port, metric, with_mask, exchange, out):
         groups = (np.arange(n) // 4).astype(np.int32)
         excl = groups[np.random.default_rng(7).integers(0, n, nq)].astype(np.int32) if with_mask else None
         idx = ShardedIndexFlat(d, metric, device=rank, exchange=exchange)
-        idx.add_global(xb)
-        lo, hi = shard_bounds(n, world, rank)
+        # shards proportional to measured speed for one of the cases (weights agree on every rank: all-gathered)
+        weights = idx.calibrate(batch=256, rows=20000, seconds=0.05, k=k) if (with_mask and exchange == "peer") else None
+        if weights is not None:
+            assert len(weights) == world and abs(sum(weights) - 1.0) < 1e-9 and min(weights) > 0.5 / world
+            weights = [w * (1.3 if r == 0 else 1.0) for r, w in enumerate(weights)]      # and visibly uneven
+        idx.add_global(xb, weights=weights)
+        lo, hi = shard_bounds(n, world, rank, weights)
         assert idx.local.ntotal == hi - lo and idx.ntotal == n
         if with_mask:
             idx.set_groups_global(groups)

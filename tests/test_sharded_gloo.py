@@ -101,6 +101,22 @@ def test_two_rank_sharded_search_equals_unsharded(metric, with_mask):
     assert len(out) == world
 
 
+def test_weighted_shard_bounds_cover_rows_exactly():
+    """Shards proportional to measured GPU speed (ShardedIndexFlat.calibrate): contiguous, complete, tile-aligned."""
+    from textreact_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 1000, 60001, 16_000_000):
+        for w in ([1, 1], [0.26, 0.24, 0.25, 0.25], [1.07, 1.0, 0.93, 1.0, 1.0, 1.0, 1.02, 0.98]):
+            W = len(w)
+            b = [shard_bounds(n, W, r, w) for r in range(W)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(W - 1)) and all(lo <= hi for lo, hi in b)
+            if n >= W * 256:
+                assert all(lo % 256 == 0 for lo, _ in b)
+    lo, hi = shard_bounds(16_000_000, 4, 0, [0.26, 0.24, 0.25, 0.25])
+    assert (lo, hi) == (0, 4_160_000)
+    assert shard_bounds(1000, 4, 2, None) == (500, 750)
+
+
 def test_shard_bounds_cover_rows_exactly():
     from textreact_b200.sharded import shard_bounds
     for n in (0, 1, 7, 1000, 16_000_000):

@@ -23,9 +23,27 @@ from . import _lib
 from .index import IndexFlat, _stream_handle, merge_topk
 
 
-def shard_bounds(n, world, rank):
-    """Contiguous, near-even split: rows [lo, hi) of shard ``rank``."""
-    return rank * n // world, (rank + 1) * n // world
+def shard_bounds(n, world, rank, weights=None, align=256):
+    """Contiguous split: rows [lo, hi) of shard ``rank``.  Near-even by default; with ``weights`` (one positive number
+    per rank, e.g. the measured relative speed of each GPU) the shard sizes are proportional to them, interior
+    boundaries rounded to a multiple of ``align`` rows (the scoring kernel's corpus tile)."""
+    if weights is None:
+        return rank * n // world, (rank + 1) * n // world
+    w = [float(v) for v in weights]
+    assert len(w) == world and all(v > 0 for v in w), "one positive weight per rank"
+    total = sum(w)
+
+    def edge(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n
+        e = int(round(n * sum(w[:r]) / total))
+        if align > 1 and n >= world * align:
+            e = int(round(e / align)) * align
+        return min(max(e, 0), n)
+    lo, hi = edge(rank), edge(rank + 1)
+    return lo, max(lo, hi)
 
 
 class PendingSearch:
@@ -130,11 +148,45 @@ class ShardedIndexFlat:
     def ntotal(self):
         return self._ntotal_global
 
-    def add_global(self, x):
-        """Every rank is handed the same [N, d] array (or a lazily sliced view); keeps its slice."""
+    def add_global(self, x, weights=None):
+        """Every rank is handed the same [N, d] array (or a lazily sliced view); keeps its slice -- near-even, or
+        proportional to ``weights`` (see ``calibrate``)."""
         n = x.shape[0]
-        lo, hi = shard_bounds(n, self.world, self.rank)
+        lo, hi = shard_bounds(n, self.world, self.rank, weights)
         self.add_shard(x[lo:hi], lo, n)
+
+    def calibrate(self, batch=8192, rows=1_000_000, seconds=1.5, k=100):
+        """Relative scoring speed of every rank's GPU, measured: each rank searches a throw-away random index for
+        ``seconds`` and the device time of the scoring passes per corpus row is all-gathered.  Returns one weight per
+        rank (sum 1), for ``shard_bounds(..., weights=)`` / ``add_global(..., weights=)``.  B200s under the 1 kW power
+        cap differ by several per cent in sustained tensor throughput; with equal shards every step waits for the
+        slowest one, with shards proportional to speed they finish together.  Collective (one all-gather)."""
+        import time
+        assert self._on_cuda, "calibrate() measures the CUDA engine"
+        dev = torch.device("cuda", self.local.device)
+        probe = IndexFlat(self.d, self.metric_type, device=self.local.device)
+        try:
+            g = torch.Generator(device=dev)
+            g.manual_seed(97 + self.rank)
+            for c0 in range(0, rows, 250_000):
+                probe.add(torch.randn((min(250_000, rows - c0), self.d), generator=g, device=dev))
+            q = torch.randn((batch, self.d), generator=g, device=dev)
+            for _ in range(3):
+                probe.search(q, k)
+            s0, t0, n = probe.stats(), time.perf_counter(), 0
+            while n < 3 or time.perf_counter() - t0 < seconds:
+                probe.search(q, k)
+                n += 1
+            s1 = probe.stats()
+            nb = max(1, s1["timed_batches"] - s0["timed_batches"])
+            ms = (s1["sum_prefilter_ms"] - s0["sum_prefilter_ms"] + s1["sum_sample_ms"] - s0["sum_sample_ms"]) / nb
+        finally:
+            probe.close()
+        mine = torch.tensor([ms / rows], dtype=torch.float64, device=dev)
+        allr = torch.empty((self.world,), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine, group=self.group)
+        speed = 1.0 / allr.clamp(min=1e-12)
+        return [float(v) for v in (speed / speed.sum()).tolist()]
 
     def add_shard(self, x_local, lo, n_global):
         """This rank's rows are global rows [lo, lo + len(x_local))."""
