@@ -132,6 +132,21 @@ typedef struct trx_search_params_t {
 int trx_search_ex(trx_index* idx, const float* xq, int64_t nq, int k, const trx_search_params_t* params,
                   float* D, int64_t* I, void* cuda_stream);
 
+/* The search of ONE batch (nq <= max_batch) in two halves, for the row-sharded multi-GPU mode (SURVEY.md section 8e;
+ * no reference counterpart).  A shard that answers alone must rescore enough candidates to certify ITS top-k; but most
+ * of a shard's top-k never reaches the global top-k.  So:
+ *   trx_search_begin   prefilter up to the masked, sorted candidate lists; payload[q] (device, [nq, nb + 1] floats) =
+ *                      the nb best prefilter scores of query q on this shard, then the query's certificate slack eps
+ *   (the shards exchange the payloads: trx_exchange_floor -> floor[nq])
+ *   trx_search_finish  exact rescore of the candidates at or above floor[q] only, then the usual results -- with
+ *                      possibly fewer than k rows per query (padded with -1): exactly this shard's members of the
+ *                      global top-k and a few more.  floor NULL: the plain local top-k.
+ * The k-way merge of the shards' results is the exact global top-k.  The queries / mask are copied by begin; nothing
+ * else may be searched on the index between the two calls. */
+int trx_search_begin(trx_index* idx, const float* xq, int64_t nq, int k, const trx_search_params_t* params, int nb,
+                     float* payload, void* cuda_stream);
+int trx_search_finish(trx_index* idx, const float* floor, float* D, int64_t* I, void* cuda_stream);
+
 /* trx_search with the stored rows [row0, row0+nq) as the queries -- the reference's train->train search
  * (query_fps is train_fps, retrieve/retrieve_faiss.py:114-115) without sending the corpus to the device twice. */
 int trx_search_self(trx_index* idx, int64_t row0, int64_t nq, int k, const int32_t* excl,
@@ -188,6 +203,12 @@ int trx_exchange_merge(trx_exchange* ex, int metric, const float* D_local, const
  * every rank must take part in every exchange (nq_out may be 0). */
 int trx_exchange_merge_slice(trx_exchange* ex, int metric, const float* D_local, const int64_t* I_local, int64_t nq, int k,
                              int64_t q0, int64_t nq_out, float* D, int64_t* I, void* cuda_stream);
+/* Bounds exchange of the two-phase search (trx_search_begin / trx_search_finish): every rank passes the payload its
+ * trx_search_begin produced ([nq, nb + 1] floats: the nb best prefilter scores of every query on this shard, then the
+ * query's certificate slack eps) and receives floor[nq]: a prefilter score below which no row of the GLOBAL top-k can
+ * lie (k-th largest of the world * nb exchanged scores - 2 * the largest eps).  Collective, stream-ordered. */
+int trx_exchange_floor(trx_exchange* ex, const float* payload, int64_t nq, int nb, int k, float* floor_out,
+                       void* cuda_stream);
 void trx_exchange_destroy(trx_exchange* ex);
 
 /* Raw bf16 scoring GEMM on the tcgen05 path, for tests and profiling:

@@ -640,3 +640,56 @@ def test_engine_against_real_faiss_when_it_is_installed():
         oracle.check_parity(D, I, xb, xq, 100, metric)
         assert (I == If).mean() > 0.995
         np.testing.assert_allclose(D, Df, rtol=2e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("shards,with_mask", [(2, False), (4, True), (8, False)])
+def test_two_phase_search_of_row_shards_on_one_gpu(metric, shards, with_mask):
+    """The two-phase local search of the row-sharded mode (trx_search_begin -> bounds exchange -> trx_search_finish),
+    with all the shards on ONE device so that it runs on a one-GPU box: every shard exports its best prefilter scores,
+    the floor computed from them lets each shard rescore only what can reach the GLOBAL top-k, and the k-way merge of
+    the (short, padded) per-shard results must be the exact unsharded answer.  Also: far fewer rows are rescored."""
+    import torch
+    trx = _engine()
+    from textreact_b200.index import merge_topk
+    from textreact_b200.sharded import floor_from_payloads, shard_bounds
+    n, d, nq, k = 120_000, 256, 300, 50
+    xb, xq = util.gaussian(n, d, 801), util.gaussian(nq, d, 802)
+    groups = (np.arange(n) // 3).astype(np.int32)
+    excl = groups[np.random.default_rng(803).integers(0, n, nq)].astype(np.int32) if with_mask else None
+    nb = 24
+    idx, rescored = [], {}
+    for g in range(shards):
+        lo, hi = shard_bounds(n, shards, g)
+        ix = trx.IndexFlat(d, metric)
+        ix.add(xb[lo:hi])
+        ix.set_id_offset(lo)
+        if with_mask:
+            ix.set_groups(groups[lo:hi])
+        idx.append(ix)
+    xq_t = torch.from_numpy(xq).cuda()
+    ex_t = None if excl is None else torch.from_numpy(excl).cuda()
+    for mode in ("two_phase", "plain"):
+        r0 = sum(ix.stats()["rescored"] for ix in idx)
+        if mode == "two_phase":
+            payloads = torch.stack([ix.search_begin(xq_t, k, nb, exclude=ex_t) for ix in idx])
+            assert payloads.shape == (shards, nq, nb + 1)
+            floor = floor_from_payloads(payloads, nb, k)
+            res = [ix.search_finish(floor) for ix in idx]
+            padded = sum(int((I < 0).sum().item()) for _, I in res)
+            assert padded > 0.3 * shards * nq * k          # most of a shard's local top-k is not even produced
+        else:
+            res = [ix.search(xq_t, k, exclude=ex_t) for ix in idx]
+        rescored[mode] = sum(ix.stats()["rescored"] for ix in idx) - r0
+        Dm, Im = merge_topk(torch.stack([r[0] for r in res]), torch.stack([r[1] for r in res]), metric)
+        oracle.check_parity(Dm.cpu().numpy(), Im.cpu().numpy(), xb, xq, k, metric, groups if with_mask else None, excl)
+    assert rescored["two_phase"] < 0.6 * rescored["plain"], rescored
+    # a begin must be finished before anything else is searched; finish(None) is the plain local top-k
+    idx[0].search_begin(xq_t, k, nb)
+    with pytest.raises(RuntimeError, match="two-phase"):
+        idx[0].search(xq_t, k)
+    D0, I0 = idx[0].search_finish(None)
+    D1, I1 = idx[0].search(xq_t, k)
+    np.testing.assert_array_equal(I0.cpu().numpy(), I1.cpu().numpy())
+    for ix in idx:
+        ix.close()

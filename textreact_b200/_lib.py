@@ -48,6 +48,9 @@ SIGNATURES = {
     "trx_set_groups": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     "trx_search": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp]),
     "trx_search_ex": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(TrxSearchParams), _vp, _vp, _vp]),
+    "trx_search_begin": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(TrxSearchParams), ctypes.c_int, _vp, _vp]),
+    "trx_search_finish": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "trx_exchange_floor": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     "trx_search_self": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, _vp]),
     "trx_set_row_attr": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
     "trx_reconstruct": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),

@@ -148,8 +148,21 @@ struct RescoreArgs {
     const float* eps_acc;  // fp32 summation slack per query (subtracted from fb_thr)
     const int32_t* qmap;   // nullable: output row / fb_list value of query i is qmap[i]
     uint64_t* counters;                     // [0] rescored rows [1] uncertified [2] overflow [3] candidates
+    // two-phase (row-sharded) search: the lists were filtered and sorted by launch_bounds (no masks / sort here), and
+    // floor[q] (nullable, prefilter domain) is a score no row of the GLOBAL top-k can fall below: rows under it are
+    // dropped, and a list that is rescored down to the floor is complete -- possibly with fewer than k results.
+    int presorted; const float* floor;
 };
 int launch_rescore(const RescoreArgs& a, cudaStream_t st);
+// First half of a two-phase search: per query, the candidate list with the masks applied, sorted by prefilter score
+// (written back in place, cand_cnt = eligible count), and payload[q] = { its nb best prefilter scores (-inf padded),
+// eps[q] } -- what the shards exchange to bound the global k-th score.  Overflowed lists are left alone (-inf row).
+struct BoundsArgs {
+    Cand* cand; uint32_t* cand_cnt; int cap; int64_t nq;
+    const int32_t* groups; const int32_t* excl; const int32_t* attr; int32_t attr_below;
+    const float* eps; int nb; float* payload;   // [nq][nb + 1]
+};
+int launch_bounds(const BoundsArgs& a, cudaStream_t st);
 // dynamic shared memory one K4 CTA needs; the prefilter paths are only taken when it fits kK4MaxSmem
 constexpr size_t kK4MaxSmem = 200 * 1024;
 inline size_t k4_smem_bytes(int cap, int d, int k, bool dedup) {

@@ -349,28 +349,37 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(Resco
     const int P = next_pow2(n_c);
     __syncthreads();
     uint32_t my_valid = 0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        uint64_t key = KEY_SENTINEL;
-        if (i < n_c) {
+    if (a.presorted) {   // launch_bounds already applied the masks and sorted the list
+        for (int i = threadIdx.x; i < n_c; i += blockDim.x) {
             Cand c = a.cand[q * (int64_t)a.cap + i];
-            bool ok = !(ex >= 0 && __ldg(a.groups + c.row) == ex);
-            if (a.attr != nullptr && __ldg(a.attr + c.row) >= a.attr_below) ok = false;
-            if (ok) { key = pack_key(c.score, (uint32_t)c.row); my_valid++; }
+            keys[i] = pack_key(c.score, (uint32_t)c.row);
         }
-        keys[i] = key;
+        if (threadIdx.x == 0) s_valid = (uint32_t)n_c;
+    } else {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            uint64_t key = KEY_SENTINEL;
+            if (i < n_c) {
+                Cand c = a.cand[q * (int64_t)a.cap + i];
+                bool ok = !(ex >= 0 && __ldg(a.groups + c.row) == ex);
+                if (a.attr != nullptr && __ldg(a.attr + c.row) >= a.attr_below) ok = false;
+                if (ok) { key = pack_key(c.score, (uint32_t)c.row); my_valid++; }
+            }
+            keys[i] = key;
+        }
+        if (my_valid) atomicAdd(&s_valid, my_valid);
     }
-    if (my_valid) atomicAdd(&s_valid, my_valid);
     if (METRIC == TRX_METRIC_L2) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) qn2_part += __shfl_xor_sync(0xffffffffu, qn2_part, o);
         if (lane == 0) atomicAdd(&s_qn2, qn2_part);
     }
-    bitonic_sort_u64(keys, P);  // (prefilter score desc, row asc); masked / padding last
-    const int n_valid = (int)s_valid;
+    if (a.presorted) __syncthreads();
+    else bitonic_sort_u64(keys, P);  // (prefilter score desc, row asc); masked / padding last
+    int n_valid = (int)s_valid;
     const float qn2 = s_qn2;
     const float thr = a.thr[q];
     const float eps = a.eps[q];
-    const bool complete = !(thr > -INFINITY);  // every eligible row is in the list
+    bool complete = !(thr > -INFINITY);  // every eligible row is in the list
 
     // keys[0 .. n_valid) are sorted by prefilter score, best first: number of them scoring at least `cut`
     auto count_at_least = [&](float cut) {
@@ -392,6 +401,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(Resco
     if (a.dedup || n_valid <= k) m = (2 * k + 56 + 7) & ~7;
     else m = (count_at_least(key_score(keys[k - 1]) - 1.15f * eps) + 7) & ~7;
     if (m < k + 8) m = k + 8;
+    // Row-sharded search: no row scoring under floor[q] can be in the GLOBAL top-k (the shards together hold k rows
+    // that beat it, rigorously), and rows the prefilter did not list score <= thr.  If the floor is above thr the rows
+    // down to the floor are all this shard can contribute: rescore exactly those -- usually far fewer than the local
+    // top-k would need -- and the list is complete.
+    if (a.floor != nullptr && !a.dedup) {
+        const float fl = a.floor[q];
+        if (fl > thr) {
+            const int n_eff = count_at_least(fl);
+            if (n_eff <= m) { n_valid = n_eff; complete = true; }
+        }
+    }
     if (m > n_valid || complete) m = n_valid;
     bool certified = false;
     for (;;) {
@@ -492,6 +512,59 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(Resco
             Iq[j] = (int64_t)key_id(key) + a.id_offset;
         } else { Dq[j] = fill; Iq[j] = -1; }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// first half of a two-phase (row-sharded) search: filter + sort the candidate lists, export the best scores
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k4_bounds_kernel(BoundsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ uint32_t s_valid;
+    const int64_t q = blockIdx.x;
+    float* out = a.payload + q * (a.nb + 1);
+    const uint32_t cnt_raw = a.cand_cnt[q];
+    if (threadIdx.x == 0) out[a.nb] = a.eps[q];
+    if (cnt_raw > (uint32_t)a.cap) {   // overflowed list: no bound from this shard; the second half sends it to the scan
+        for (int j = threadIdx.x; j < a.nb; j += blockDim.x) out[j] = -INFINITY;
+        return;
+    }
+    const int n_c = (int)cnt_raw;
+    const int32_t ex = (a.excl != nullptr && a.groups != nullptr) ? a.excl[q] : -1;
+    if (threadIdx.x == 0) s_valid = 0;
+    const int P = next_pow2(n_c);
+    __syncthreads();
+    uint32_t my_valid = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t key = KEY_SENTINEL;
+        if (i < n_c) {
+            Cand c = a.cand[q * (int64_t)a.cap + i];
+            bool ok = !(ex >= 0 && __ldg(a.groups + c.row) == ex);
+            if (a.attr != nullptr && __ldg(a.attr + c.row) >= a.attr_below) ok = false;
+            if (ok) { key = pack_key(c.score, (uint32_t)c.row); my_valid++; }
+        }
+        keys[i] = key;
+    }
+    if (my_valid) atomicAdd(&s_valid, my_valid);
+    bitonic_sort_u64(keys, P);
+    const int n_valid = (int)s_valid;
+    for (int i = threadIdx.x; i < n_valid; i += blockDim.x) {
+        Cand c; c.score = key_score(keys[i]); c.row = (int32_t)key_id(keys[i]);
+        a.cand[q * (int64_t)a.cap + i] = c;
+    }
+    for (int j = threadIdx.x; j < a.nb; j += blockDim.x) out[j] = j < n_valid ? key_score(keys[j]) : -INFINITY;
+    if (threadIdx.x == 0) a.cand_cnt[q] = (uint32_t)n_valid;
+}
+
+int launch_bounds(const BoundsArgs& a, cudaStream_t st) {
+    if (a.nq <= 0) return TRX_OK;
+    const size_t smem = (size_t)a.cap * 8;
+    if (smem > kK4MaxSmem) { set_error("k4 bounds: cap=%d exceeds shared memory", a.cap); return TRX_EINVAL; }
+    TRX_CUDA(cudaFuncSetAttribute(k4_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k4_bounds_kernel<<<(unsigned)a.nq, 256, smem, st>>>(a);
+    count_launch();
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
 }
 
 int launch_rescore(const RescoreArgs& a, cudaStream_t st) {

@@ -105,6 +105,63 @@ __global__ void __launch_bounds__(256) k5_peer_merge_kernel(int metric, PeerView
     }
 }
 
+// Bounds exchange of the two-phase search: every rank published payload[q] = { its nb best PREFILTER scores of query
+// q, eps[q] }.  The k-th largest of the G*nb scores is a lower bound on the k-th largest prefilter score over the whole
+// corpus (it is the k-th largest of a subset); the rows behind those k scores have exact scores >= score - eps_max, so
+// the global k-th EXACT score is >= kth - eps_max, and a row whose prefilter score is below  kth - 2 eps_max  has an
+// exact score below that: it cannot be in the global top-k.  floor[q] = kth - 2 eps_max (minus rounding slack), or
+// -inf when the shards hold fewer than k candidates between them.
+struct PeerPayload {
+    const float* p[kMaxWorld];
+};
+
+__global__ void __launch_bounds__(256) k5_peer_floor_kernel(PeerPayload pp, const unsigned long long* my_flags,
+                                                            unsigned long long want, int G, int nb, int k,
+                                                            float* __restrict__ floor_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ float s_eps[kMaxWorld];
+    const int64_t q = blockIdx.x;
+    const int total = G * nb;
+    int P = 2;
+    while (P < total) P <<= 1;
+    if (threadIdx.x < G) {
+        uint64_t t0 = 0;
+        uint32_t polls = 0;
+        while (ld_acquire_sys(my_flags + threadIdx.x) < want) {
+            __nanosleep(64);
+            if ((++polls & 0x3ffu) == 0) {
+                uint64_t t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 30ull * 1000 * 1000 * 1000) __trap();
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t key = KEY_SENTINEL;
+        if (i < total) {
+            const int g = i / nb, j = i - g * nb;
+            const float v = *reinterpret_cast<const volatile float*>(pp.p[g] + q * (nb + 1) + j);   // peer load
+            if (v > -INFINITY) key = pack_key(v, (uint32_t)i);
+        }
+        keys[i] = key;
+    }
+    if (threadIdx.x < G) s_eps[threadIdx.x] = *reinterpret_cast<const volatile float*>(pp.p[threadIdx.x] + q * (nb + 1) + nb);
+    bitonic_sort_u64(keys, P);
+    if (threadIdx.x == 0) {
+        float fl = -INFINITY;
+        if (k <= total && keys[k - 1] != KEY_SENTINEL) {
+            float em = 0.f;
+            for (int g = 0; g < G; g++) em = fmaxf(em, s_eps[g]);
+            fl = key_score(keys[k - 1]) - 2.f * em * 1.00001f;
+            fl -= fabsf(fl) * 1e-6f + 1e-30f;
+        }
+        floor_out[q] = fl;
+    }
+}
+
 }  // namespace trx
 
 using namespace trx;
@@ -229,6 +286,39 @@ int trx_exchange_merge_slice(trx_exchange* ex, int metric, const float* D_local,
                                                                   want, ex->world, q0, k, D, I);
         count_launch();
     }
+    TRX_CUDA(cudaGetLastError());
+    ex->step++;
+    return TRX_OK;
+}
+
+int trx_exchange_floor(trx_exchange* ex, const float* payload, int64_t nq, int nb, int k, float* floor_out,
+                       void* cuda_stream) {
+    if (!ex || !payload || !floor_out || nq <= 0 || nb <= 0 || k <= 0) { set_error("bad argument"); return TRX_EINVAL; }
+    if (!ex->connected && ex->world > 1) { set_error("exchange: not connected"); return TRX_EINVAL; }
+    const size_t bytes = (size_t)nq * (nb + 1) * 4;
+    if (bytes > slot_bytes(ex->max_entries)) { set_error("exchange: bounds payload of %zu bytes exceeds the export slot", bytes); return TRX_EINVAL; }
+    ExDeviceGuard g(ex->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int s = (int)(ex->step & 1ull);
+    // the payload travels in the same double-buffered export slots (and under the same flag protocol) as the lists
+    TRX_CUDA(cudaMemcpyAsync(const_cast<int64_t*>(slot_I(ex->base, ex->max_entries, s)), payload, bytes, cudaMemcpyDeviceToDevice, st));
+    PeerFlags pf{};
+    PeerPayload pp{};
+    for (int p = 0; p < ex->world; p++) {
+        pf.f[p] = reinterpret_cast<unsigned long long*>(ex->peer_base[p]);
+        pp.p[p] = reinterpret_cast<const float*>(slot_I(ex->peer_base[p], ex->max_entries, s));
+    }
+    const unsigned long long want = ex->step + 1;
+    k5_publish_kernel<<<1, 32, 0, st>>>(pf, ex->world, ex->rank, want);
+    count_launch();
+    int P = 2;
+    while (P < ex->world * nb) P <<= 1;
+    const size_t smem = (size_t)P * 8;
+    if (smem > 200 * 1024) { set_error("exchange: world*nb=%d too large", ex->world * nb); return TRX_EINVAL; }
+    TRX_CUDA(cudaFuncSetAttribute(k5_peer_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_peer_floor_kernel<<<(unsigned)nq, 256, smem, st>>>(pp, reinterpret_cast<const unsigned long long*>(ex->base), want,
+                                                          ex->world, nb, k, floor_out);
+    count_launch();
     TRX_CUDA(cudaGetLastError());
     ex->step++;
     return TRX_OK;

@@ -103,6 +103,12 @@ __global__ void second_pass_prep_kernel(const int32_t* __restrict__ list, int n,
     }
 }
 
+// two-phase search on the exact path: no bound from this shard (payload row = -inf scores, eps 0)
+__global__ void fill_payload_kernel(float* __restrict__ payload, int64_t nq, int nb) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * (nb + 1)) payload[i] = (i % (nb + 1)) == nb ? 0.f : -INFINITY;
+}
+
 __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ list, int n,
                                   int32_t* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,6 +140,7 @@ struct BatchWs {
     // the batch in flight
     int64_t B = 0; int path = 0;
     bool timed = false;                                    // ev[0..3] were recorded for the batch in flight
+    bool two_phase = false; int tp_k = 0; int32_t tp_attr = INT32_MAX; int tp_dedup = 0;   // between search_begin and _finish
     const float* qdev = nullptr; const int32_t* exdev = nullptr;
     float* D = nullptr; int64_t* I = nullptr; bool out_dev = false, out_pinned = false;
 };
@@ -503,7 +510,7 @@ static int prepare_prefilter(trx_index* ix, BatchWs& w, int k) {
 
 // The prefilter pipeline of one batch, stream work only:
 //   K1 batch begin -> K2<SLOTMAX> on the sample -> thresholds -> main pass (K2<THRESH> + scatter | K3) -> K4 -> count
-static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
+static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st, bool with_rescore = true) {
     const int64_t B = w.B, N = ix->ntotal;
     TRX_TRY(launch_query_prep(w.qdev, B, ix->d, ix->Kp, ix->metric, w.q16, w.qnorm2, ix->norm2_max, w.eps,
                               w.eps_acc, w.cand_cnt, w.fb_count, st));
@@ -536,6 +543,7 @@ static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st) 
         TRX_TRY(launch_stream(a, ix->sm_count, st));
     }
     if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[2], st));
+    if (!with_rescore) return TRX_OK;       // two-phase search: K4 runs in trx_search_finish, with the exchanged floor
 
     TRX_TRY(launch_rescore(rescore_args(ix, w, k), st));
     TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
@@ -545,11 +553,15 @@ static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st) 
 // Queue one batch: query upload (copy stream), every kernel, the fallback count and the results (compute
 // stream).  Nothing here waits for the GPU.
 static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev, int64_t B, int k, const int32_t* excl,
-                        bool excl_dev, float* D, int64_t* I, bool out_dev, cudaStream_t st) {
+                        bool excl_dev, float* D, int64_t* I, bool out_dev, cudaStream_t st, int bounds_nb = 0,
+                        float* payload = nullptr) {
+    const bool first_half = payload != nullptr;     // trx_search_begin: stop after the candidate lists + bounds
     const int64_t N = ix->ntotal;
     const int cap = candidate_cap(ix, k);
     TRX_TRY(ensure_ws(ix, w, (int)B, k, cap));
-    w.B = B; w.D = D; w.I = I; w.out_dev = out_dev; w.out_pinned = !out_dev && is_pinned_host_ptr(D) && is_pinned_host_ptr(I);
+    w.B = B; w.D = D; w.I = I; w.out_dev = out_dev;
+    w.out_pinned = !first_half && !out_dev && is_pinned_host_ptr(D) && is_pinned_host_ptr(I);
+    w.two_phase = false;
 
     // queries / exclusion list on the device: uploaded on the copy stream so that a (host-blocking) copy from
     // pageable memory runs while the previous batch computes
@@ -589,10 +601,41 @@ static int launch_batch(trx_index* ix, BatchWs& w, const float* xq, bool xq_dev,
     ix->st.last_path = path;
     // Small batches replay a captured graph (below); every other batch carries four event records, so that the
     // per-stage device times of the batches a caller times are available afterwards (trx_stats sums).
-    const bool graph_ok = path != TRX_PATH_EXACT && ix->graphs && B <= ix->graph_max_batch && !ix->timing &&
+    const bool graph_ok = path != TRX_PATH_EXACT && ix->graphs && B <= ix->graph_max_batch && !ix->timing && !first_half &&
                           st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
     w.timed = !graph_ok;
     if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[0], st));
+
+    if (first_half) {
+        // the caller's query / mask buffers need not outlive this call: the second half reads the workspace copies
+        if (w.qdev != w.q32) {
+            TRX_CUDA(cudaMemcpyAsync(w.q32, w.qdev, (size_t)B * ix->d * 4, cudaMemcpyDeviceToDevice, st));
+            w.qdev = w.q32;
+        }
+        if (w.exdev != nullptr && w.exdev != w.excl) {
+            TRX_CUDA(cudaMemcpyAsync(w.excl, w.exdev, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+            w.exdev = w.excl;
+        }
+        if (path == TRX_PATH_EXACT) {
+            const int64_t n = B * (bounds_nb + 1);
+            fill_payload_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(payload, B, bounds_nb);
+            count_launch();
+            TRX_CUDA(cudaGetLastError());
+            if (w.timed) { TRX_CUDA(cudaEventRecord(w.ev[1], st)); TRX_CUDA(cudaEventRecord(w.ev[2], st)); }
+        } else {
+            TRX_TRY(ensure_sample(ix, st));
+            TRX_TRY(prepare_prefilter(ix, w, k));
+            TRX_TRY(enqueue_prefilter(ix, w, k, st, false));
+            BoundsArgs ba{};
+            ba.cand = w.cand; ba.cand_cnt = w.cand_cnt; ba.cap = w.cap; ba.nq = B;
+            ba.groups = ix->has_groups ? ix->groups : nullptr; ba.excl = w.exdev;
+            ba.attr = attr_active(ix) ? ix->attr : nullptr; ba.attr_below = ix->attr_below;
+            ba.eps = w.eps; ba.nb = bounds_nb; ba.payload = payload;
+            TRX_TRY(launch_bounds(ba, st));
+        }
+        w.two_phase = true; w.tp_k = k; w.tp_attr = ix->attr_below; w.tp_dedup = ix->dedup;
+        return TRX_OK;
+    }
 
     if (path == TRX_PATH_EXACT) {
         TRX_TRY(run_exact(ix, w.qdev, w.exdev, nullptr, B, k, w.Dd, w.Id, st));
@@ -1015,6 +1058,7 @@ static int search_impl(trx_index* ix, const float* xq, int64_t nq, int k, const 
     if (nq < 0 || k <= 0) { set_error("bad nq=%lld or k=%d", (long long)nq, k); return TRX_EINVAL; }
     if (nq == 0) return TRX_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
+    if (ix->ws[0].two_phase) { set_error("a two-phase search is pending (trx_search_begin without trx_search_finish)"); return TRX_EINVAL; }
     ModeGuard modes(ix);
     const int32_t* excl = nullptr;
     if (sp) {
@@ -1081,6 +1125,78 @@ int trx_search_ex(trx_index* ix, const float* xq, int64_t nq, int k, const trx_s
                   int64_t* I, void* cuda_stream) {
     if (!params) return trx_search(ix, xq, nq, k, nullptr, D, I, cuda_stream);
     return search_impl(ix, xq, nq, k, params, D, I, cuda_stream);
+}
+
+// ---- two-phase search for the row-sharded mode -------------------------------------------------------------------
+// begin:  prefilter of ONE batch up to the (masked, sorted) candidate lists; payload[q] = the nb best prefilter scores
+//         of the query on this shard + its eps.  The shards exchange the payloads (trx_exchange_floor) ...
+// finish: ... and K4 rescores only what can still reach the GLOBAL top-k (rows at or above floor[q]): at G shards
+//         that is ~1/G of what the local top-k would need.  Results may hold fewer than k rows per query (padded);
+//         the merge of the shards' results is the exact global top-k.
+int trx_search_begin(trx_index* ix, const float* xq, int64_t nq, int k, const trx_search_params_t* sp, int nb,
+                     float* payload, void* cuda_stream) {
+    if (!ix) { set_error("null index"); return TRX_EINVAL; }
+    if (nq <= 0 || k <= 0 || nb <= 0 || !payload) { set_error("search_begin: bad nq=%lld, k=%d or nb=%d", (long long)nq, k, nb); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (nq > ix->max_batch) { set_error("search_begin takes one batch (nq=%lld > max_batch=%d)", (long long)nq, ix->max_batch); return TRX_EINVAL; }
+    if (ix->ntotal == 0) { set_error("search_begin on an empty index"); return TRX_EINVAL; }
+    if (ix->ws[0].two_phase) { set_error("search_begin: the previous two-phase search was not finished"); return TRX_EINVAL; }
+    ModeGuard modes(ix);
+    const int32_t* excl = nullptr;
+    if (sp) {
+        excl = sp->exclude;
+        ix->attr_below = sp->attr_below;
+        ix->dedup = sp->dedup_groups != 0;
+        if (sp->self_row0 >= 0) {
+            if (sp->self_row0 + nq > ix->ntotal) { set_error("search_begin: self rows out of range"); return TRX_EINVAL; }
+            xq = ix->x32 + sp->self_row0 * ix->d;
+        }
+    }
+    if (!xq) { set_error("null buffer"); return TRX_EINVAL; }
+    if (k > 2048) { set_error("k=%d exceeds the supported maximum 2048", k); return TRX_EINVAL; }
+    if (excl && !ix->has_groups) { set_error("exclude given but no groups set (trx_set_groups)"); return TRX_EINVAL; }
+    if (ix->dedup && !ix->has_groups) { set_error("dedup_groups set but no groups set (trx_set_groups)"); return TRX_EINVAL; }
+    if (ix->attr_below != INT32_MAX && !ix->has_attr) { set_error("attr_below set but no row attributes (trx_set_row_attr)"); return TRX_EINVAL; }
+    if (!is_device_ptr(payload)) { set_error("search_begin: payload must be a device pointer"); return TRX_EINVAL; }
+    DeviceGuard g(ix->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
+    ix->st.searches++;
+    TRX_TRY(ensure_group_stats(ix));
+    return launch_batch(ix, ix->ws[0], xq, is_device_ptr(xq), nq, k, excl, is_device_ptr(excl), nullptr, nullptr, true, st,
+                        nb, payload);
+}
+
+int trx_search_finish(trx_index* ix, const float* floor, float* D, int64_t* I, void* cuda_stream) {
+    if (!ix || !D || !I) { set_error("bad argument"); return TRX_EINVAL; }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    BatchWs& w = ix->ws[0];
+    if (!w.two_phase) { set_error("search_finish without search_begin"); return TRX_EINVAL; }
+    w.two_phase = false;
+    if (floor && !is_device_ptr(floor)) { set_error("search_finish: floor must be a device pointer"); return TRX_EINVAL; }
+    const bool out_dev = is_device_ptr(D);
+    if (out_dev != is_device_ptr(I)) { set_error("D and I must both be host or both be device pointers"); return TRX_EINVAL; }
+    ModeGuard modes(ix);
+    ix->attr_below = w.tp_attr; ix->dedup = w.tp_dedup;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
+    const int k = w.tp_k;
+    w.D = D; w.I = I; w.out_dev = out_dev;
+    w.out_pinned = !out_dev && is_pinned_host_ptr(D) && is_pinned_host_ptr(I);
+    if (w.path == TRX_PATH_EXACT) {
+        TRX_TRY(run_exact(ix, w.qdev, w.exdev, nullptr, w.B, k, w.Dd, w.Id, st));
+        *w.h_nfb = 0;
+    } else {
+        RescoreArgs ra = rescore_args(ix, w, k);
+        ra.presorted = 1; ra.floor = floor;
+        TRX_TRY(launch_rescore(ra, st));
+        TRX_CUDA(cudaMemcpyAsync(w.h_nfb, w.fb_count, 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (w.timed) TRX_CUDA(cudaEventRecord(w.ev[3], st));
+    TRX_TRY(send_results(ix, w, k, st));
+    TRX_CUDA(cudaEventRecord(w.done, st));
+    int rc = finish_batch(ix, w, k, st);
+    if (rc != TRX_OK) cudaStreamSynchronize(st);
+    return rc;
 }
 
 int trx_set_option(trx_index* ix, const char* key, double v) {

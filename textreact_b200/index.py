@@ -157,6 +157,38 @@ class IndexFlat:
         del keep, ex_keep
         return out
 
+    # -- two-phase search (row-sharded multi-GPU mode; see include/trx.h) ---------------------
+    def search_begin(self, x, k, nb, *, exclude=None, attr_below=None):
+        """First half for ONE batch of CUDA-tensor queries: prefilter up to the masked, sorted candidate lists.
+        Returns the payload to exchange: float32 CUDA [nq, nb + 1] = the nb best prefilter scores per query, then eps."""
+        ptr, nq, keep, on_dev = _as_f32_matrix(x, self.d)
+        assert on_dev, "search_begin takes CUDA tensors"
+        ex_ptr, ex_keep = (None, None)
+        if exclude is not None:
+            ex_ptr, ex_keep = _as_i32_vector(exclude, nq, "exclude")
+        payload = torch.empty((nq, int(nb) + 1), dtype=torch.float32, device=keep.device)
+        sp = _lib.TrxSearchParams(ex_ptr, 2147483647 if attr_below is None else int(attr_below), 0, -1)
+        _lib.check(self._L.trx_search_begin(self._h, ptr, nq, int(k), ctypes.byref(sp), int(nb), payload.data_ptr(),
+                                            _stream_handle(keep.device)), "search_begin")
+        self._pending = (nq, int(k), keep.device)
+        del keep, ex_keep
+        return payload
+
+    def search_finish(self, floor=None, *, D=None, I=None):
+        """Second half: exact rescore of the candidates at or above ``floor`` (float32 CUDA [nq]; None = plain local
+        top-k).  Returns (D, I) CUDA tensors; rows that cannot reach the global top-k are missing (-1 padded)."""
+        nq, k, dev = self._pending
+        self._pending = None
+        Dt = D if D is not None else torch.empty((nq, k), dtype=torch.float32, device=dev)
+        It = I if I is not None else torch.empty((nq, k), dtype=torch.int64, device=dev)
+        fptr = None
+        if floor is not None:
+            assert floor.is_cuda and floor.dtype == torch.float32 and floor.shape == (nq,) and floor.is_contiguous()
+            fptr = floor.data_ptr()
+        _lib.check(self._L.trx_search_finish(self._h, fptr, Dt.data_ptr(), It.data_ptr(), _stream_handle(dev)),
+                   "search_finish")
+        return Dt, It
+
     def reset(self):
         _lib.check(self._L.trx_reset(self._h), "reset")
 

@@ -46,6 +46,23 @@ def shard_bounds(n, world, rank, weights=None, align=256):
     return lo, max(lo, hi)
 
 
+def floor_from_payloads(g, nb, k):
+    """[G, nq, nb + 1] gathered bounds payloads (``IndexFlat.search_begin``) -> floor[nq]: the k-th largest of the
+    G * nb exchanged prefilter scores is a lower bound on the global k-th prefilter score, the rows behind it score
+    exactly at least that minus eps, so a row whose prefilter score is below  kth - 2 max(eps)  cannot be in the
+    global top-k.  -inf where the shards hold fewer than k candidates between them.  (What ``trx_exchange_floor``
+    computes inside its peer-memory kernel.)"""
+    G, nq = g.shape[0], g.shape[1]
+    scores = g[:, :, :nb].permute(1, 0, 2).reshape(nq, -1)
+    eps = g[:, :, nb].max(dim=0).values
+    if scores.shape[1] < k:
+        return torch.full((nq,), float("-inf"), dtype=torch.float32, device=g.device)
+    kth = torch.topk(scores, k, dim=1).values[:, k - 1]
+    floor = kth - 2.0 * eps * 1.00001
+    floor = floor - floor.abs() * 1e-6 - 1e-30
+    return torch.where(torch.isfinite(kth), floor, torch.full_like(floor, float("-inf"))).contiguous()
+
+
 class PendingSearch:
     """Handle of a ``search_async``: the merged (D, I) become valid for the caller's stream in ``result()``."""
 
@@ -127,7 +144,8 @@ class ReplicatedIndexFlat:
 
 
 class ShardedIndexFlat:
-    def __init__(self, d, metric, *, group=None, local_factory=None, merge_fn=None, device=None, exchange=None):
+    def __init__(self, d, metric, *, group=None, local_factory=None, merge_fn=None, device=None, exchange=None,
+                 two_phase=None):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -138,11 +156,19 @@ class ShardedIndexFlat:
         self._ntotal_global = 0
         self._lo = 0
         self._xstream = None          # side stream of the exchange step (CUDA only)
+        self._xev = None              # ... and the event of the last exchange queued on it
         # "peer": all-gather fused into the merge kernel over NVLink peer memory (CUDA IPC, K5p); "nccl": NCCL
         # all-gather + K5.  Default: peer on the CUDA engine, NCCL for the CPU test doubles / when mapping fails.
         self._exchange_mode = exchange or os.environ.get("TRX_EXCHANGE") or ("peer" if self._on_cuda and merge_fn is None else "nccl")
         self._peer = None             # trx_exchange handle
         self._peer_entries = 0
+        # Two-phase local search (CUDA engine only): the shards first exchange their best PREFILTER scores, which
+        # bounds the global k-th score from below, and each shard then rescores only the candidates that can still
+        # reach the global top-k -- ~1/G of what certifying its own top-k would take (K4 does not shrink with G
+        # otherwise).  TRX_TWO_PHASE=0 / two_phase=False: every shard computes its full local top-k.
+        if two_phase is None:
+            two_phase = os.environ.get("TRX_TWO_PHASE", "1") != "0"
+        self._two_phase = bool(two_phase) and self._on_cuda and merge_fn is None
 
     @property
     def ntotal(self):
@@ -234,7 +260,10 @@ class ShardedIndexFlat:
             if exclude is not None and not (isinstance(exclude, torch.Tensor) and exclude.is_cuda):
                 exclude = torch.as_tensor(np.ascontiguousarray(exclude, dtype=np.int32)).to(dev)
         kw = {} if attr_below is None else {"attr_below": attr_below}
-        D, I = self.local.search(xq, k, exclude=exclude, **kw)       # complete on return (host-synchronised)
+        if self._two_phase and self.world > 1 and isinstance(xq, torch.Tensor) and xq.is_cuda:
+            D, I = self._local_search_two_phase(xq, k, exclude, kw)
+        else:
+            D, I = self.local.search(xq, k, exclude=exclude, **kw)   # complete on return (host-synchronised)
         if not isinstance(D, torch.Tensor):
             D, I = torch.from_numpy(D), torch.from_numpy(I)
         assert result in ("full", "slice")
@@ -249,9 +278,47 @@ class ShardedIndexFlat:
             Dm, Im = self.exchange(D, I, result=result)
             ev = torch.cuda.Event()
             ev.record(self._xstream)
+            self._xev = ev
         for t in (D, I):
             t.record_stream(self._xstream)
         return PendingSearch(Dm, Im, ev, as_numpy)
+
+    def bounds_width(self, k):
+        """Prefilter scores per query every shard contributes to the bounds exchange: its expected share of the
+        global top-k (k / G) plus four standard deviations -- any width gives a valid (lower) bound."""
+        share = k / self.world
+        return int(min(k, max(8, -(-int(share + 4.0 * share ** 0.5 + 4.0) // 8) * 8)))
+
+    def _local_search_two_phase(self, xq, k, exclude, kw):
+        mb = int(self.local.get_option("max_batch"))
+        nb = self.bounds_width(k)
+        if self._xev is not None:      # the bounds exchange shares the export slots with the merge: keep them in order
+            torch.cuda.current_stream(xq.device).wait_event(self._xev)
+        outs = []
+        for q0 in range(0, xq.shape[0], mb):
+            xc = xq[q0:q0 + mb].contiguous()
+            ec = None if exclude is None else exclude[q0:q0 + mb]
+            payload = self.local.search_begin(xc, k, nb, exclude=ec, **kw)
+            outs.append(self.local.search_finish(self.exchange_floor(payload, nb, k)))
+        if len(outs) == 1:
+            return outs[0]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
+    def exchange_floor(self, payload, nb, k):
+        """The bounds exchange: every rank's [nq, nb + 1] payload -> floor[nq], a prefilter score below which no row
+        of the global top-k can lie (k-th largest of the G * nb exchanged scores - 2 * the largest eps).  Peer mode:
+        one kernel over NVLink peer memory (trx_exchange_floor); NCCL mode: all-gather + torch top-k."""
+        nq = payload.shape[0]
+        if self._exchange_mode == "peer":
+            ex = self._peer_exchange(nq, k, payload.device)
+            if ex is not None:
+                floor = torch.empty((nq,), dtype=torch.float32, device=payload.device)
+                _lib.check(_lib.lib().trx_exchange_floor(ex, payload.data_ptr(), nq, nb, k, floor.data_ptr(),
+                                                         _stream_handle(payload.device)), "exchange_floor")
+                return floor
+        g = torch.empty((self.world,) + tuple(payload.shape), dtype=payload.dtype, device=payload.device)
+        dist.all_gather_into_tensor(g, payload.contiguous(), group=self.group)
+        return floor_from_payloads(g, nb, k)
 
     def _peer_exchange(self, nq, k, device):
         """(Re)build the peer-memory exchange for at least nq*k entries.  Collective: every rank takes the same
