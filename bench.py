@@ -378,8 +378,12 @@ def main():
                     help="N > 1: 'slice' = the merge is sharded too, rank g ends up with the merged top-k of queries "
                          "[g*B/N, (g+1)*B/N) (1/N of the exchange traffic; every answer exists on one rank); 'full' = every "
                          "rank ends up with every query's result")
-    ap.add_argument("--shards", default="calibrated", choices=["calibrated", "even"],
-                    help="N > 1: shard sizes proportional to each GPU's measured scoring speed (default), or equal")
+    ap.add_argument("--shards", default="even", choices=["calibrated", "even"],
+                    help="N > 1: equal shards (default), or sizes proportional to each GPU's measured scoring speed "
+                         "(ShardedIndexFlat.calibrate; measured: the intrinsic spread is +-1.5 %, no gain at N = 8)")
+    ap.add_argument("--two-phase", type=int, default=1,
+                    help="N > 1: 1 = the shards exchange their best prefilter scores first and rescore only what can reach "
+                         "the global top-k (default); 0 = every shard computes its full local top-k")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1 only: row-sharded corpus (north_star's contract, default) or the whole corpus on every "
                          "GPU with the queries split (measurement beside it)")
@@ -429,10 +433,11 @@ def main():
     else:
         sidx = None
         local = trx.IndexFlatIP(D_MODEL, device=local_rank)
-    # Shards: B200s under the 1 kW cap differ by several per cent in sustained tensor throughput and every step waits
-    # for the slowest rank, so each rank first measures its scoring speed on a throw-away index (1.5 s) and the rows are
-    # split in proportion (ShardedIndexFlat.calibrate); --shards even gives the plain N/G split.
+    # Shards: equal by default.  --shards calibrated: each rank first measures its scoring speed on a throw-away index
+    # (1.5 s) and the rows are split in proportion (ShardedIndexFlat.calibrate).
     weights = None
+    if sidx is not None:
+        sidx._two_phase = bool(args.two_phase)
     if sidx is not None and args.shards == "calibrated":
         weights = sidx.calibrate(batch=batch)
     lo, hi = shard_bounds(rows, world, rank, weights)
@@ -663,6 +668,7 @@ def main():
         multi = {"shards": {"policy": args.shards, "speed_weights": weights,
                             "rows_per_rank": [shard_bounds(rows, world, r, weights)[1] - shard_bounds(rows, world, r, weights)[0]
                                               for r in range(world)]},
+                 "two_phase": bool(sidx._two_phase),
                  "local_ms_per_rank": [round(float(v), 3) for v in allr[:, 0].tolist()],
                  "k2_ms_per_rank": [round(float(v), 3) for v in allr[:, 1].tolist()],
                  "k4_ms_per_rank": [round(float(v), 3) for v in allr[:, 2].tolist()],

@@ -652,12 +652,13 @@ def test_two_phase_search_of_row_shards_on_one_gpu(metric, shards, with_mask):
     import torch
     trx = _engine()
     from textreact_b200.index import merge_topk
-    from textreact_b200.sharded import floor_from_payloads, shard_bounds
+    from textreact_b200.sharded import bounds_width, floor_from_payloads, shard_bounds
     n, d, nq, k = 120_000, 256, 300, 50
     xb, xq = util.gaussian(n, d, 801), util.gaussian(nq, d, 802)
     groups = (np.arange(n) // 3).astype(np.int32)
     excl = groups[np.random.default_rng(803).integers(0, n, nq)].astype(np.int32) if with_mask else None
-    nb = 24
+    nb = bounds_width(k, shards)
+    assert nb * shards >= k
     idx, rescored = [], {}
     for g in range(shards):
         lo, hi = shard_bounds(n, shards, g)
@@ -677,13 +678,13 @@ def test_two_phase_search_of_row_shards_on_one_gpu(metric, shards, with_mask):
             floor = floor_from_payloads(payloads, nb, k)
             res = [ix.search_finish(floor) for ix in idx]
             padded = sum(int((I < 0).sum().item()) for _, I in res)
-            assert padded > 0.3 * shards * nq * k          # most of a shard's local top-k is not even produced
+            assert padded > (1.0 - 1.7 / shards) * shards * nq * k     # most of a shard's local top-k is never produced
         else:
             res = [ix.search(xq_t, k, exclude=ex_t) for ix in idx]
         rescored[mode] = sum(ix.stats()["rescored"] for ix in idx) - r0
         Dm, Im = merge_topk(torch.stack([r[0] for r in res]), torch.stack([r[1] for r in res]), metric)
         oracle.check_parity(Dm.cpu().numpy(), Im.cpu().numpy(), xb, xq, k, metric, groups if with_mask else None, excl)
-    assert rescored["two_phase"] < 0.6 * rescored["plain"], rescored
+    assert rescored["two_phase"] < (0.9 if shards == 2 else 0.6) * rescored["plain"], rescored
     # a begin must be finished before anything else is searched; finish(None) is the plain local top-k
     idx[0].search_begin(xq_t, k, nb)
     with pytest.raises(RuntimeError, match="two-phase"):

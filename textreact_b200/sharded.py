@@ -63,6 +63,13 @@ def floor_from_payloads(g, nb, k):
     return torch.where(torch.isfinite(kth), floor, torch.full_like(floor, float("-inf"))).contiguous()
 
 
+def bounds_width(k, world):
+    """Prefilter scores per query every shard contributes to the bounds exchange: its expected share of the global
+    top-k (k / world) plus four standard deviations -- any width gives a valid (lower) bound; at least k in total."""
+    share = k / world
+    return int(min(k, max(8, -(-int(share + 4.0 * share ** 0.5 + 4.0) // 8) * 8)))
+
+
 class PendingSearch:
     """Handle of a ``search_async``: the merged (D, I) become valid for the caller's stream in ``result()``."""
 
@@ -283,15 +290,9 @@ class ShardedIndexFlat:
             t.record_stream(self._xstream)
         return PendingSearch(Dm, Im, ev, as_numpy)
 
-    def bounds_width(self, k):
-        """Prefilter scores per query every shard contributes to the bounds exchange: its expected share of the
-        global top-k (k / G) plus four standard deviations -- any width gives a valid (lower) bound."""
-        share = k / self.world
-        return int(min(k, max(8, -(-int(share + 4.0 * share ** 0.5 + 4.0) // 8) * 8)))
-
     def _local_search_two_phase(self, xq, k, exclude, kw):
         mb = int(self.local.get_option("max_batch"))
-        nb = self.bounds_width(k)
+        nb = bounds_width(k, self.world)
         if self._xev is not None:      # the bounds exchange shares the export slots with the merge: keep them in order
             torch.cuda.current_stream(xq.device).wait_event(self._xev)
         outs = []
