@@ -211,6 +211,14 @@ int trx_exchange_floor(trx_exchange* ex, const float* payload, int64_t nq, int n
                        void* cuda_stream);
 void trx_exchange_destroy(trx_exchange* ex);
 
+/* Plain device buffers for callers without a CUDA runtime of their own (a C program, a numpy-only script): the
+ * device-pointer forms of the calls above (trx_search_begin / _finish, trx_merge_topk, ...) can then be used without
+ * torch.  trx_device_copy moves bytes host <-> device in any direction and is synchronous. */
+#include <stddef.h>
+int trx_device_malloc(int device, size_t bytes, void** out);
+int trx_device_free(void* p);
+int trx_device_copy(void* dst, const void* src, size_t bytes);
+
 /* Raw bf16 scoring GEMM on the tcgen05 path, for tests and profiling:
  * out[nq, n] = bf16(xq) . bf16(x_row)  (fp32 accumulate) over rows [row0, row0+n). */
 int trx_debug_scores_umma(trx_index* idx, const float* xq, int64_t nq, int64_t row0, int64_t n,

@@ -71,6 +71,9 @@ SIGNATURES = {
     "trx_exchange_merge_slice": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
                                                 ctypes.c_int64, _vp, _vp, _vp]),
     "trx_exchange_destroy": (None, [_vp]),
+    "trx_device_malloc": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    "trx_device_free": (ctypes.c_int, [_vp]),
+    "trx_device_copy": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "trx_debug_scores_umma": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _vp, _vp]),
     "trx_last_error": (ctypes.c_char_p, []),
     "trx_version": (ctypes.c_char_p, []),

@@ -1293,6 +1293,24 @@ int trx_merge_topk(int metric, const float* Dg, const int64_t* Ig, int G, int64_
     return launch_merge(metric, Dg, Ig, G, nq, k, D, I, (cudaStream_t)cuda_stream);
 }
 
+// Plain device buffers for callers that have no CUDA runtime of their own (C programs, numpy-only test drivers).
+int trx_device_malloc(int device, size_t bytes, void** out) {
+    if (!out) { set_error("out is null"); return TRX_EINVAL; }
+    DeviceGuard g(device);
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return TRX_ENOMEM; }
+    return TRX_OK;
+}
+int trx_device_free(void* p) {
+    if (p) TRX_CUDA(cudaFree(p));
+    return TRX_OK;
+}
+int trx_device_copy(void* dst, const void* src, size_t bytes) {   // host <-> device in any direction, synchronous
+    if (bytes && (!dst || !src)) { set_error("null buffer"); return TRX_EINVAL; }
+    TRX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return TRX_OK;
+}
+
 int trx_debug_scores_umma(trx_index* ix, const float* xq, int64_t nq, int64_t row0, int64_t n, float* out,
                           void* cuda_stream) {
     if (!ix || !xq || !out || nq <= 0 || n <= 0 || row0 < 0 || row0 + n > ix->ntotal) { set_error("bad argument"); return TRX_EINVAL; }
