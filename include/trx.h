@@ -213,7 +213,8 @@ void trx_exchange_destroy(trx_exchange* ex);
 
 /* Plain device buffers for callers without a CUDA runtime of their own (a C program, a numpy-only script): the
  * device-pointer forms of the calls above (trx_search_begin / _finish, trx_merge_topk, ...) can then be used without
- * torch.  trx_device_copy moves bytes host <-> device in any direction and is synchronous. */
+ * torch.  trx_device_copy moves bytes host <-> device in any direction; it first waits for all work queued on the
+ * current device (the index's streams are non-blocking) and is complete on return. */
 #include <stddef.h>
 int trx_device_malloc(int device, size_t bytes, void** out);
 int trx_device_free(void* p);

@@ -1307,6 +1307,7 @@ int trx_device_free(void* p) {
 }
 int trx_device_copy(void* dst, const void* src, size_t bytes) {   // host <-> device in any direction, synchronous
     if (bytes && (!dst || !src)) { set_error("null buffer"); return TRX_EINVAL; }
+    TRX_CUDA(cudaDeviceSynchronize());     // the index's streams are non-blocking: wait for whatever produces `src`
     TRX_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
     return TRX_OK;
 }
