@@ -694,3 +694,22 @@ def test_two_phase_search_of_row_shards_on_one_gpu(metric, shards, with_mask):
     np.testing.assert_array_equal(I0.cpu().numpy(), I1.cpu().numpy())
     for ix in idx:
         ix.close()
+
+
+def test_add_npy_streams_the_reference_fingerprint_cache(tmp_path):
+    """retrieve_faiss.py:106-110 caches the train fingerprints with np.save into `train_fp.pkl`; add_npy ingests such a
+    file chunk by chunk (memory-mapped, raw int8 / int64 over PCIe) and gives the same index as add(np.load(...))."""
+    trx = _engine()
+    for fps in (util.fingerprints(7000, 256, 901), util.count_fingerprints(5000, 128, 902), util.gaussian(6000, 96, 903)):
+        path = tmp_path / "train_fp.pkl"
+        with open(path, "wb") as f:
+            np.save(f, fps)
+        a, b = trx.IndexFlatL2(fps.shape[1]), trx.IndexFlatL2(fps.shape[1])
+        assert a.add_npy(str(path), chunk_rows=1500) == len(fps) and a.ntotal == len(fps)
+        b.add(fps)
+        Da, Ia = a.search(fps[:40], 7)
+        Db, Ib = b.search(fps[:40], 7)
+        np.testing.assert_array_equal(Ia, Ib)
+        np.testing.assert_array_equal(Da, Db)
+        np.testing.assert_array_equal(a.reconstruct_n(0, 50), np.ascontiguousarray(fps[:50], dtype=np.float32))
+        a.close(); b.close()

@@ -111,6 +111,17 @@ class IndexFlat:
         _lib.check(self._L.trx_add(self._h, ptr, n), "add")
         del keep
 
+    def add_npy(self, path, chunk_rows=262144):
+        """``index.add(np.load(path))`` without holding the array in host memory: the file (what ``np.save`` wrote --
+        the reference's fingerprint cache ``train_fp.pkl`` is one, retrieve/retrieve_faiss.py:106-110 -- or a
+        Tevatron embedding dump) is memory-mapped and streamed to the device in chunks, any numeric dtype."""
+        a = np.load(path, mmap_mode="r")
+        assert a.ndim == 2 and a.shape[1] == self.d, f"expected shape [n, {self.d}], got {a.shape}"
+        self.reserve(self.ntotal + a.shape[0])
+        for r0 in range(0, a.shape[0], int(chunk_rows)):
+            self.add(np.ascontiguousarray(a[r0:r0 + int(chunk_rows)]))
+        return a.shape[0]
+
     def search(self, x, k, *, D=None, I=None, exclude=None, attr_below=None, dedup=False, params=None):
         assert k > 0
         ptr, nq, keep, on_dev = _as_f32_matrix(x, self.d)
