@@ -7,7 +7,12 @@ README.md:44-47 whose output enters through retrieve/convert_format.py:7-16).
 
 PARITY UNPINNED.  ``faiss`` is not vendored, not pinned (absent from environment.yml) and
 not importable in this image; the reference has no tests or golden vectors for this path
-(SURVEY.md section 4 / 8c).  This file restates FAISS's published algorithm instead:
+(SURVEY.md section 4 / 8c); the one attempt to fetch faiss-cpu on a GPU box found no index
+reachable either (profiles/round2_a_try_faiss_on_gpu_box.log).  tests/test_oracle.py checks
+this restatement against two unrelated implementations that ARE here (torch/MKL matmul + topk,
+scikit-learn's brute-force kNN) and, automatically, against the real faiss wherever it imports
+(tests/golden/make_faiss_golden.py then produces real-FAISS known-answer vectors).
+This file restates FAISS's published algorithm:
 
 * ``search_blas``  -- the nq >= 20 path: fp32 ``sgemm`` over query-block x database-block
   tiles (FAISS defaults 4096 x 1024; any blocking gives the same scores because the

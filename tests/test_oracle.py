@@ -154,3 +154,21 @@ def test_oracle_against_real_faiss_when_it_is_installed():
     Df, If = index.search(np.ascontiguousarray(fb[:30], dtype="float32"), 5)
     Do, Io = oracle.search(fb, fb[:30], 5, 1)
     np.testing.assert_array_equal(Do, Df)                      # integer distances: exact
+
+
+def test_oracle_against_scikit_learn_brute_force():
+    """A third, unrelated implementation (scikit-learn's brute-force kNN: pairwise distances in its own Cython/BLAS
+    code + argpartition) agrees with the restatement on L2 -- ids wherever ranks are separated, distances to 1e-5 --
+    and on 0/1 fingerprints, where distances are integers, exactly (ids compared as tie-free sets)."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    xb, xq = util.gaussian(20000, 96, 41), util.gaussian(64, 96, 42)
+    nn = sk.NearestNeighbors(n_neighbors=10, algorithm="brute", metric="sqeuclidean").fit(xb.astype(np.float64))
+    Ds, Is = nn.kneighbors(xq.astype(np.float64))
+    Do, Io = oracle.search(xb, xq, 10, 1)
+    assert (Io == Is).mean() > 0.999
+    np.testing.assert_allclose(Do, Ds, rtol=2e-5, atol=2e-4)
+    fb = util.fingerprints(4000, 128, 43).astype(np.float64)
+    nn = sk.NearestNeighbors(n_neighbors=5, algorithm="brute", metric="sqeuclidean").fit(fb)
+    Ds, Is = nn.kneighbors(fb[:30])
+    Do, Io = oracle.search(fb, fb[:30], 5, 1)
+    np.testing.assert_array_equal(Do, Ds.astype(np.float32))              # integer distances: exact
