@@ -244,6 +244,14 @@ static int grow(trx_index* ix, int64_t need) {
     return TRX_OK;
 }
 
+// CTA-pair tiling (256-query tiles) or single-CTA tiling (128-query tiles) for a batch of B queries.  Pairs win from
+// 129 queries on -- except where the last pair tile would be half empty and there are few tiles: 257..384 queries run
+// as three 128-row tiles (measured at 4M x 768: 1.95 ms vs 2.08 ms as two pair tiles; profiles/round2_p_sweep.json).
+static bool use_pair_tiling(const trx_index* ix, int64_t B) {
+    if (!ix->umma_pair || B < ix->pair_min_batch) return false;
+    return !(B > 256 && B <= 384);
+}
+
 static bool attr_active(const trx_index* ix) { return ix->has_attr && ix->attr_below != INT32_MAX; }
 
 // fraction of rows that pass the attribute filter
@@ -494,7 +502,7 @@ static int prepare_prefilter(trx_index* ix, BatchWs& w, int k) {
     const int64_t B = w.B, N = ix->ntotal;
     w.T = effective_target(ix, k);
     w.r = std::max(1, (w.T + ix->sample_rate / 2) / ix->sample_rate);
-    w.pair = ix->umma_pair && B >= ix->pair_min_batch;
+    w.pair = use_pair_tiling(ix, B);
     w.S = umma_num_slices(ix->ns, B, ix->sm_count, w.pair);
     size_t need = (size_t)B * w.S * 32;
     if (need > w.slots_elems) { dfree(w.slots); TRX_TRY(dmalloc(&w.slots, need)); w.slots_elems = need; ix->gen++; }
@@ -753,7 +761,7 @@ static int finish_batch(trx_index* ix, BatchWs& w, int k, cudaStream_t st) {
                 TRX_CUDA(cudaGetLastError());
                 UmmaArgs u{};
                 u.q16 = ix->q16fb; u.nq = nl; u.x16 = ix->x16; u.n = N; u.Kp = ix->Kp;
-                u.pair = ix->umma_pair && nl >= ix->pair_min_batch;
+                u.pair = use_pair_tiling(ix, nl);
                 u.mode = 1; u.thr = ix->thr2; u.cand = w.cand; u.cand_cnt = w.cand_cnt; u.cap = w.cap;
                 const int nlogs = umma_grid(nl, N, ix->sm_count, u.pair, false) * 128;
                 // the band [s_k - eps, s_k] can hold several times the first pass's target: size the logs for a full list
