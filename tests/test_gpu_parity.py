@@ -692,6 +692,11 @@ def test_two_phase_search_of_row_shards_on_one_gpu(metric, shards, with_mask):
     D0, I0 = idx[0].search_finish(None)
     D1, I1 = idx[0].search(xq_t, k)
     np.testing.assert_array_equal(I0.cpu().numpy(), I1.cpu().numpy())
+    # a mutation between the halves abandons the pending search (its candidate lists describe the old rows)
+    idx[0].search_begin(xq_t, k, nb)
+    idx[0].add(xb[:10])
+    with pytest.raises(RuntimeError, match="without search_begin"):
+        idx[0].search_finish(None)
     for ix in idx:
         ix.close()
 

@@ -252,6 +252,10 @@ static bool use_pair_tiling(const trx_index* ix, int64_t B) {
     return !(B > 256 && B <= 384);
 }
 
+// Anything that changes the stored rows or their side data abandons a pending two-phase search: its candidate lists
+// refer to what was there at trx_search_begin (trx_search_finish then fails cleanly instead of reading freed rows).
+static void abandon_two_phase(trx_index* ix) { ix->ws[0].two_phase = false; ix->ws[1].two_phase = false; }
+
 static bool attr_active(const trx_index* ix) { return ix->has_attr && ix->attr_below != INT32_MAX; }
 
 // fraction of rows that pass the attribute filter
@@ -902,6 +906,7 @@ void trx_destroy(trx_index* ix) {
 int trx_reset(trx_index* ix) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
+    abandon_two_phase(ix);
     ix->gen++;
     DeviceGuard g(ix->device);
     TRX_CUDA(cudaDeviceSynchronize());
@@ -917,6 +922,7 @@ int trx_metric(const trx_index* ix) { return ix ? ix->metric : -1; }
 int trx_reserve(trx_index* ix, int64_t n) {
     if (!ix || n < 0) { set_error("bad argument"); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
+    abandon_two_phase(ix);
     DeviceGuard g(ix->device);
     ix->gen++;
     return grow(ix, n);
@@ -926,6 +932,7 @@ int trx_add(trx_index* ix, const float* x, int64_t n) {
     if (!ix || n < 0 || (n > 0 && !x)) { set_error("bad argument"); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
+    abandon_two_phase(ix);
     ix->gen++;
     DeviceGuard g(ix->device);
     TRX_TRY(grow(ix, ix->ntotal + n));
@@ -949,6 +956,7 @@ int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
     if (es == 0) { set_error("add_typed: unknown dtype %d", dtype); return TRX_EINVAL; }
     if (n == 0) return TRX_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
+    abandon_two_phase(ix);
     ix->gen++;
     DeviceGuard g(ix->device);
     TRX_TRY(grow(ix, ix->ntotal + n));
@@ -992,6 +1000,7 @@ int trx_add_typed(trx_index* ix, const void* x, int64_t n, int dtype) {
 int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
+    abandon_two_phase(ix);
     ix->group_max = 0; ix->group_avg = 1.0; ix->gen++;
     if (gsrc == nullptr) { ix->has_groups = false; return TRX_OK; }
     if (n != ix->ntotal) { set_error("set_groups: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
@@ -1005,6 +1014,7 @@ int trx_set_groups(trx_index* ix, const int32_t* gsrc, int64_t n) {
 int trx_set_row_attr(trx_index* ix, const int32_t* asrc, int64_t n) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
+    abandon_two_phase(ix);
     ix->gen++;
     if (asrc == nullptr) { ix->has_attr = false; ix->attr_sorted.clear(); return TRX_OK; }
     if (n != ix->ntotal) { set_error("set_row_attr: n=%lld != ntotal=%lld", (long long)n, (long long)ix->ntotal); return TRX_EINVAL; }
@@ -1049,6 +1059,7 @@ int trx_reconstruct(trx_index* ix, int64_t row0, int64_t n, float* out) {
 int trx_set_id_offset(trx_index* ix, int64_t offset) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
+    abandon_two_phase(ix);
     ix->id_offset = offset; ix->gen++;
     return TRX_OK;
 }
@@ -1144,7 +1155,7 @@ int trx_search_ex(trx_index* ix, const float* xq, int64_t nq, int k, const trx_s
 int trx_search_begin(trx_index* ix, const float* xq, int64_t nq, int k, const trx_search_params_t* sp, int nb,
                      float* payload, void* cuda_stream) {
     if (!ix) { set_error("null index"); return TRX_EINVAL; }
-    if (nq <= 0 || k <= 0 || nb <= 0 || !payload) { set_error("search_begin: bad nq=%lld, k=%d or nb=%d", (long long)nq, k, nb); return TRX_EINVAL; }
+    if (nq <= 0 || k <= 0 || nb <= 0 || nb > 4096 || !payload) { set_error("search_begin: bad nq=%lld, k=%d or nb=%d", (long long)nq, k, nb); return TRX_EINVAL; }
     std::lock_guard<std::mutex> lock(ix->mu);
     if (nq > ix->max_batch) { set_error("search_begin takes one batch (nq=%lld > max_batch=%d)", (long long)nq, ix->max_batch); return TRX_EINVAL; }
     if (ix->ntotal == 0) { set_error("search_begin on an empty index"); return TRX_EINVAL; }

@@ -188,6 +188,7 @@ class IndexFlat:
     def search_finish(self, floor=None, *, D=None, I=None):
         """Second half: exact rescore of the candidates at or above ``floor`` (float32 CUDA [nq]; None = plain local
         top-k).  Returns (D, I) CUDA tensors; rows that cannot reach the global top-k are missing (-1 padded)."""
+        assert getattr(self, "_pending", None) is not None, "search_finish without search_begin"
         nq, k, dev = self._pending
         self._pending = None
         Dt = D if D is not None else torch.empty((nq, k), dtype=torch.float32, device=dev)
