@@ -657,6 +657,22 @@ def main():
         mine = torch.tensor([stages["total"], stages["prefilter"], stages["rescore"], stages["sample"]], device=dev)
         allr = torch.empty((world, 4), device=dev)
         dist.all_gather_into_tensor(allr, mine)
+        # two-phase local search on / off, alternating in this process (run-to-run differences between launches are
+        # larger than the effect): median ms/step of 3 timed regions each, and the rows K4 rescored per query per shard
+        ab = {"on": [], "off": []}
+        resc = {}
+        keep_tp = sidx._two_phase
+        for rep in range(3):
+            for name, flag in (("on", True), ("off", False)):
+                sidx._two_phase = flag
+                step_dev(0); step_dev(1)
+                r0 = local.stats()["rescored"]
+                ab[name].append(timed(step_dev, args.steps) / args.steps)
+                resc[name] = (local.stats()["rescored"] - r0) / (args.steps * batch)
+        sidx._two_phase = keep_tp
+        two_phase_ab = {"ms_per_step_on": sorted(ab["on"])[1], "ms_per_step_off": sorted(ab["off"])[1],
+                        "all_ms_on": [round(v, 3) for v in ab["on"]], "all_ms_off": [round(v, 3) for v in ab["off"]],
+                        "rescored_rows_per_query_per_shard_on": resc["on"], "rescored_rows_per_query_per_shard_off": resc["off"]}
         # the same steps without the exchange: what the coupling of the ranks (exchange + waiting for the slowest) costs
         def step_local(i):
             local.search(queries[i % len(queries)], K)
@@ -680,7 +696,7 @@ def main():
         multi = {"shards": {"policy": args.shards, "speed_weights": weights,
                             "rows_per_rank": [shard_bounds(rows, world, r, weights)[1] - shard_bounds(rows, world, r, weights)[0]
                                               for r in range(world)]},
-                 "two_phase": bool(sidx._two_phase),
+                 "two_phase": bool(sidx._two_phase), "two_phase_ab": two_phase_ab,
                  "local_ms_per_rank": [round(float(v), 3) for v in allr[:, 0].tolist()],
                  "k2_ms_per_rank": [round(float(v), 3) for v in allr[:, 1].tolist()],
                  "k4_ms_per_rank": [round(float(v), 3) for v in allr[:, 2].tolist()],
