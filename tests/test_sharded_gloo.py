@@ -161,3 +161,31 @@ def test_two_rank_query_sharded_replicas():
         p.join(120)
         assert p.exitcode == 0
     assert len(out) == world
+
+
+def test_floor_from_payloads_is_a_valid_lower_bound():
+    """The bounds exchange of the two-phase search, host restatement (what trx_exchange_floor computes in its kernel):
+    floor = k-th largest of the G * nb exchanged prefilter scores - 2 * max eps, -inf when fewer than k are finite.
+    Property checked on random shards: no row of the true global top-k (by exact score, |exact - prefilter| <= eps)
+    has a prefilter score below the floor."""
+    from textreact_b200.sharded import bounds_width, floor_from_payloads
+    rng = np.random.default_rng(3)
+    G, nq, k, rows = 4, 50, 20, 400
+    nb = bounds_width(k, G)
+    assert nb * G >= k and nb <= k and bounds_width(100, 8) == 32 and bounds_width(100, 1) == 100
+    exact = rng.standard_normal((G, nq, rows)).astype(np.float32) * 5
+    eps = rng.uniform(0.05, 0.2, (G, nq)).astype(np.float32)
+    pre = exact + rng.uniform(-1, 1, exact.shape).astype(np.float32) * eps[:, :, None]      # |pre - exact| <= eps
+    top = -np.sort(-pre, axis=2)[:, :, :nb]
+    payload = torch.from_numpy(np.concatenate([top, eps[:, :, None]], axis=2))
+    floor = floor_from_payloads(payload, nb, k).numpy()
+    allx = exact.transpose(1, 0, 2).reshape(nq, -1)
+    allp = pre.transpose(1, 0, 2).reshape(nq, -1)
+    for q in range(nq):
+        topk = np.argsort(-allx[q])[:k]
+        assert (allp[q][topk] >= floor[q]).all()
+    # the bound is not vacuous: it cuts most of every shard's rows
+    assert (allp < floor[:, None]).mean() > 0.8
+    # too few finite scores -> no bound
+    payload[:, 0, :nb] = float("-inf")
+    assert floor_from_payloads(payload, nb, k)[0] == float("-inf")
