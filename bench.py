@@ -460,7 +460,7 @@ def main():
     want_base = "strong_base" in legs
     local.reserve(16_000_000 if want_base else hi - lo)
     for key, env in (("target_candidates", "TRX_TARGET"), ("sample_rate", "TRX_SAMPLE_RATE"), ("path", "TRX_PATH"), ("thr_bias", "TRX_THR_BIAS"),
-                     ("umma_pair", "TRX_UMMA_PAIR"), ("second_pass", "TRX_SECOND_PASS")):
+                     ("umma_pair", "TRX_UMMA_PAIR"), ("second_pass", "TRX_SECOND_PASS"), ("thr_margin", "TRX_THR_MARGIN")):
         if os.environ.get(env):          # tuning knobs for experiments; defaults are what is reported
             local.set_option(key, float(os.environ[env]))
     seed = 1234 + (0 if replicas else rank)

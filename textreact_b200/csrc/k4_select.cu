@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* scratch 
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowKthSmem = 8192;
 __global__ void __launch_bounds__(512) row_kth_kernel(const float* __restrict__ s, int64_t ld, int64_t n, int r,
-                                                      float* __restrict__ thr) {
+                                                      float* __restrict__ thr, const float* __restrict__ margin) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t bc[4];
     __shared__ uint32_t scratch[33];
@@ -123,12 +123,13 @@ __global__ void __launch_bounds__(512) row_kth_kernel(const float* __restrict__ 
     }
     uint32_t key, gt;
     block_radix_select(row, n, (uint32_t)r, hist, bc, key, gt);
-    if (threadIdx.x == 0) thr[blockIdx.x] = key2f(key);
+    if (threadIdx.x == 0) thr[blockIdx.x] = key2f(key) - (margin ? margin[blockIdx.x] : 0.f);
 }
 
-int launch_row_kth(const float* s, int64_t ld, int64_t n, int64_t nq, int r, float* thr, cudaStream_t st) {
+int launch_row_kth(const float* s, int64_t ld, int64_t n, int64_t nq, int r, float* thr, cudaStream_t st,
+                   const float* margin) {
     if (nq <= 0) return TRX_OK;
-    row_kth_kernel<<<(unsigned)nq, 512, 0, st>>>(s, ld, n, r, thr);
+    row_kth_kernel<<<(unsigned)nq, 512, 0, st>>>(s, ld, n, r, thr, margin);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;
@@ -772,7 +773,7 @@ int launch_merge(int metric, const float* Dg, const int64_t* Ig, int G, int64_t 
 // r-th largest: a slightly permissive threshold, never a wrong one (the certificate in K4 is
 // what guarantees exactness; the threshold only sizes the candidate list).
 __global__ void __launch_bounds__(256) slot_thr_kernel(const float* __restrict__ slots, int64_t nq, int S, int r,
-                                                       float* __restrict__ thr) {
+                                                       float* __restrict__ thr, const float* __restrict__ margin) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
@@ -796,14 +797,14 @@ __global__ void __launch_bounds__(256) slot_thr_kernel(const float* __restrict__
                 if (!done && v[i] == wm) { v[i] = -INFINITY; done = true; }
         }
     }
-    if (lane == 0) thr[q] = best;
+    if (lane == 0) thr[q] = best - (margin ? margin[q] : 0.f);
 }
 
-int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st) {
+int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st, const float* margin) {
     if (nq <= 0) return TRX_OK;
     if (r > 32 * S) { set_error("slot_thr: S=%d r=%d unsupported", S, r); return TRX_EINVAL; }
-    if (S > 8) return launch_row_kth(slots, (int64_t)S * 32, (int64_t)S * 32, nq, r, thr, st);  // small batches: many slices
-    slot_thr_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(slots, nq, S, r, thr);
+    if (S > 8) return launch_row_kth(slots, (int64_t)S * 32, (int64_t)S * 32, nq, r, thr, st, margin);  // small batches: many slices
+    slot_thr_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(slots, nq, S, r, thr, margin);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;

@@ -175,6 +175,7 @@ struct trx_index {
     int umma_pair = 1;      // allow the CTA-pair (cta_group::2) tiling
     int pair_min_batch = 129;  // ... for batches of at least this many queries (measured crossover)
     int pipeline = 1;       // overlap the upload / launch of batch i+1 with batch i when a call has several
+    int thr_margin = 1;     // the sampled threshold is lowered by eps(q): the margin the certificate needs (0: as sampled)
     int second_pass = 1;    // queries without a certificate: batched second tcgen05 pass with a threshold that makes
                             // the candidate list complete (0: one fp32 streaming sweep per 4 queries instead)
     int graphs = 1;         // replay the prefilter pipeline of small batches (<= graph_max_batch) as one CUDA graph
@@ -533,7 +534,7 @@ static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st, 
     u.pair = w.pair;
     u.mode = 2; u.out = w.slots;
     TRX_TRY(launch_umma(u, ix->sm_count, st));
-    TRX_TRY(launch_slot_thr(w.slots, B, w.S, std::min(w.r, 32 * w.S), w.thr, st));
+    TRX_TRY(launch_slot_thr(w.slots, B, w.S, std::min(w.r, 32 * w.S), w.thr, st, ix->thr_margin ? w.eps : nullptr));
     if (ix->thr_bias != 0.f) {
         add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.thr, (int)B, ix->thr_bias);
         count_launch();
@@ -1248,6 +1249,8 @@ int trx_set_option(trx_index* ix, const char* key, double v) {
         ix->dedup = v != 0;
     } else if (!strcmp(key, "second_pass")) {
         ix->second_pass = v != 0;
+    } else if (!strcmp(key, "thr_margin")) {
+        ix->thr_margin = v != 0;
     } else if (!strcmp(key, "graphs")) {
         ix->graphs = v != 0;
     } else if (!strcmp(key, "graph_max_batch")) {
@@ -1279,6 +1282,7 @@ int trx_get_option(const trx_index* ix, const char* key, double* v) {
     else if (!strcmp(key, "attr_below")) *v = ix->attr_below;
     else if (!strcmp(key, "dedup_groups")) *v = ix->dedup;
     else if (!strcmp(key, "second_pass")) *v = ix->second_pass;
+    else if (!strcmp(key, "thr_margin")) *v = ix->thr_margin;
     else if (!strcmp(key, "graphs")) *v = ix->graphs;
     else if (!strcmp(key, "graph_max_batch")) *v = ix->graph_max_batch;
     else if (!strcmp(key, "graph_replays")) *v = (double)ix->graph_replays;
