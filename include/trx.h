@@ -169,8 +169,8 @@ int trx_set_id_offset(trx_index* idx, int64_t offset);
 /* Tunables: "path" (TRX_PATH_*), "max_batch", "target_candidates", "sample_rate",
  * "stream_max_batch" (crossover at or below which AUTO uses the streaming kernel),
  * "umma_pair" / "pair_min_batch" (CTA-pair tiling from this batch size on),
- * "pipeline" (0: serial batches), "thr_margin" (0: candidate thresholds exactly as sampled; default 1 lowers each by
- * the query's certificate slack eps), "second_pass" (0: uncertified queries take an fp32 streaming sweep per 4 queries
+ * "pipeline" (0: serial batches), "thr_margin" (0: candidate thresholds exactly as sampled; default 1 keeps each at
+ * least 2.5 eps under the sample's estimate of the query's k-th score, the margin the certificate needs), "second_pass" (0: uncertified queries take an fp32 streaming sweep per 4 queries
  * instead of one batched second tcgen05 pass), "attr_below" (see trx_set_row_attr; 2147483647 = off),
  * "dedup_groups" (1: distinct-groups mode -- of the rows that share a group (trx_set_groups) only the best
  * one is returned, so the k results are k different texts: the consumer's deduplicate_neighbors,

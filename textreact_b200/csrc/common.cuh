@@ -123,7 +123,7 @@ int launch_stream(const StreamArgs& a, int sm_count, cudaStream_t st);
 // r-th largest value of each row of s[nq][ld] (first n entries) -> thr[nq]; rows with fewer
 // than r finite entries get -inf.
 int launch_row_kth(const float* s, int64_t ld, int64_t n, int64_t nq, int r, float* thr,
-                   cudaStream_t st, const float* margin = nullptr);
+                   cudaStream_t st, const float* margin = nullptr, int ks = 0);
 
 // Exact top-k of materialised scores s[nq][ld] ("larger is better", -inf = ineligible):
 // (score desc, id asc), padded with id -1.  negate_out: D = -score (L2).  qmap (nullable):
@@ -188,11 +188,13 @@ int umma_grid(int64_t nq, int64_t n, int sm_count, bool pair, bool slotmax);  //
 int umma_init();  // resolves cuTensorMapEncodeTiled
 int umma_num_slices(int64_t n, int64_t nq, int sm_count, bool pair);  // S of the SLOTMAX mode (out = slots[nq][S][32])
 // r-th largest of the S*32 slot maxima of each query -> thr (any S; S <= 8 stays in one warp's registers)
-// margin (nullable, per query): subtracted from the threshold.  The search passes eps(q): the certificate needs
-// s_k > thr + eps, so a threshold set eps lower buys exactly the margin the certificate asks for -- nothing on data
-// whose score spread dwarfs eps, and the end of sampled-threshold misses where eps is about one sigma of the scores.
+// margin (nullable, per query: eps(q)) and ks = ceil(k / sample rate): the ks-th largest sample score estimates the
+// query's k-th best score s_k, and the certificate needs  s_k > thr + eps.  The threshold is therefore kept at least
+// 2.5 eps under that estimate:  thr = min(r-th largest, ks-th largest - 2.5 eps).  Where the score spread dwarfs eps
+// (Gaussian data: the r-th largest is ~10 eps under the ks-th) this changes nothing; where eps is about one sigma of
+// the scores (clustered unit-norm data) it ends the misses of a threshold that the sample put too high.
 int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st,
-                    const float* margin = nullptr);
+                    const float* margin = nullptr, int ks = 0);
 
 // Exact path, distinct-groups mode: Dx/Ix [nq, kx] sorted results (global ids) -> first k group leaders per row.
 // nfound / unfinished (nullable together): round state of the widened scan (see k4_select.cu).

@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* scratch 
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowKthSmem = 8192;
 __global__ void __launch_bounds__(512) row_kth_kernel(const float* __restrict__ s, int64_t ld, int64_t n, int r,
-                                                      float* __restrict__ thr, const float* __restrict__ margin) {
+                                                      float* __restrict__ thr, const float* __restrict__ margin, int ks) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t bc[4];
     __shared__ uint32_t scratch[33];
@@ -123,13 +123,20 @@ __global__ void __launch_bounds__(512) row_kth_kernel(const float* __restrict__ 
     }
     uint32_t key, gt;
     block_radix_select(row, n, (uint32_t)r, hist, bc, key, gt);
-    if (threadIdx.x == 0) thr[blockIdx.x] = key2f(key) - (margin ? margin[blockIdx.x] : 0.f);
+    float t = key2f(key);
+    if (margin != nullptr && ks >= 1 && ks < r) {     // see launch_slot_thr: keep the threshold 2.5 eps under the estimated k-th score
+        __syncthreads();
+        uint32_t key2, gt2;
+        block_radix_select(row, n, (uint32_t)ks, hist, bc, key2, gt2);
+        t = fminf(t, key2f(key2) - 2.5f * margin[blockIdx.x]);
+    }
+    if (threadIdx.x == 0) thr[blockIdx.x] = t;
 }
 
 int launch_row_kth(const float* s, int64_t ld, int64_t n, int64_t nq, int r, float* thr, cudaStream_t st,
-                   const float* margin) {
+                   const float* margin, int ks) {
     if (nq <= 0) return TRX_OK;
-    row_kth_kernel<<<(unsigned)nq, 512, 0, st>>>(s, ld, n, r, thr, margin);
+    row_kth_kernel<<<(unsigned)nq, 512, 0, st>>>(s, ld, n, r, thr, margin, ks);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;
@@ -773,14 +780,14 @@ int launch_merge(int metric, const float* Dg, const int64_t* Ig, int G, int64_t 
 // r-th largest: a slightly permissive threshold, never a wrong one (the certificate in K4 is
 // what guarantees exactness; the threshold only sizes the candidate list).
 __global__ void __launch_bounds__(256) slot_thr_kernel(const float* __restrict__ slots, int64_t nq, int S, int r,
-                                                       float* __restrict__ thr, const float* __restrict__ margin) {
+                                                       float* __restrict__ thr, const float* __restrict__ margin, int ks) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = i < S ? slots[(q * S + i) * 32 + lane] : -INFINITY;
-    float best = -INFINITY;
+    float best = -INFINITY, best_ks = INFINITY;
     for (int it = 0; it < r; it++) {
         float m = v[0];
 #pragma unroll
@@ -789,6 +796,7 @@ __global__ void __launch_bounds__(256) slot_thr_kernel(const float* __restrict__
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
         best = wm;
+        if (it == ks - 1) best_ks = wm;
         uint32_t owners = __ballot_sync(0xffffffffu, m == wm);
         if (lane == __ffs(owners) - 1) {  // remove one instance
             bool done = false;
@@ -797,14 +805,15 @@ __global__ void __launch_bounds__(256) slot_thr_kernel(const float* __restrict__
                 if (!done && v[i] == wm) { v[i] = -INFINITY; done = true; }
         }
     }
-    if (lane == 0) thr[q] = best - (margin ? margin[q] : 0.f);
+    if (lane == 0) thr[q] = (margin != nullptr && ks >= 1 && ks < r) ? fminf(best, best_ks - 2.5f * margin[q]) : best;
 }
 
-int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st, const float* margin) {
+int launch_slot_thr(const float* slots, int64_t nq, int S, int r, float* thr, cudaStream_t st, const float* margin,
+                    int ks) {
     if (nq <= 0) return TRX_OK;
     if (r > 32 * S) { set_error("slot_thr: S=%d r=%d unsupported", S, r); return TRX_EINVAL; }
-    if (S > 8) return launch_row_kth(slots, (int64_t)S * 32, (int64_t)S * 32, nq, r, thr, st, margin);  // small batches: many slices
-    slot_thr_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(slots, nq, S, r, thr, margin);
+    if (S > 8) return launch_row_kth(slots, (int64_t)S * 32, (int64_t)S * 32, nq, r, thr, st, margin, ks);  // small batches: many slices
+    slot_thr_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(slots, nq, S, r, thr, margin, ks);
     count_launch();
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;

@@ -175,7 +175,7 @@ struct trx_index {
     int umma_pair = 1;      // allow the CTA-pair (cta_group::2) tiling
     int pair_min_batch = 129;  // ... for batches of at least this many queries (measured crossover)
     int pipeline = 1;       // overlap the upload / launch of batch i+1 with batch i when a call has several
-    int thr_margin = 1;     // the sampled threshold is lowered by eps(q): the margin the certificate needs (0: as sampled)
+    int thr_margin = 1;     // the sampled threshold is kept 2.5 eps(q) under the sample's estimate of the k-th score (0: as sampled)
     int second_pass = 1;    // queries without a certificate: batched second tcgen05 pass with a threshold that makes
                             // the candidate list complete (0: one fp32 streaming sweep per 4 queries instead)
     int graphs = 1;         // replay the prefilter pipeline of small batches (<= graph_max_batch) as one CUDA graph
@@ -534,7 +534,8 @@ static int enqueue_prefilter(trx_index* ix, BatchWs& w, int k, cudaStream_t st, 
     u.pair = w.pair;
     u.mode = 2; u.out = w.slots;
     TRX_TRY(launch_umma(u, ix->sm_count, st));
-    TRX_TRY(launch_slot_thr(w.slots, B, w.S, std::min(w.r, 32 * w.S), w.thr, st, ix->thr_margin ? w.eps : nullptr));
+    TRX_TRY(launch_slot_thr(w.slots, B, w.S, std::min(w.r, 32 * w.S), w.thr, st, ix->thr_margin ? w.eps : nullptr,
+                            (k + ix->sample_rate - 1) / ix->sample_rate));
     if (ix->thr_bias != 0.f) {
         add_bias_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(w.thr, (int)B, ix->thr_bias);
         count_launch();
