@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrx.so")
+LIB_PATH = os.environ.get("TRX_LIBTRX") or os.path.join(_HERE, "libtrx.so")   # TRX_LIBTRX: a variant build (experiments)
 
 TRX_OK, TRX_EINVAL, TRX_ENOMEM, TRX_ECUDA, TRX_ENODEV = 0, 1, 2, 3, 4
 PATH_AUTO, PATH_EXACT, PATH_STREAM, PATH_UMMA = 0, 1, 2, 3

@@ -12,6 +12,19 @@
 
 #include "common.cuh"
 
+// Gather shape of the K4 rescore loop, compile-time knobs for measurement.  Round 2 measured unroll 2/3/6 x RW 2/3/4 x
+// min-blocks 2/3 at C2: K4 stays at 0.73-0.75 ms whatever the shape -- the gather is not what bounds it (the candidate
+// sort and the per-CTA prologue are); the defaults are round 1's.
+#ifndef K4_UNROLL
+#define K4_UNROLL 2
+#endif
+#ifndef K4_RW
+#define K4_RW 3
+#endif
+#ifndef K4_MINBLOCKS
+#define K4_MINBLOCKS 3
+#endif
+
 namespace trx {
 
 // ---------------------------------------------------------------------------------------------
@@ -280,7 +293,8 @@ __device__ __forceinline__ void exact_score_warp_n(const float* const (&xr)[RW],
 #pragma unroll
         for (int r = 0; r < RW; r++) acc[r] = 0.f;
         const float4* q4 = reinterpret_cast<const float4*>(sq);
-#pragma unroll 2
+        constexpr int kGatherUnroll = K4_UNROLL;
+#pragma unroll kGatherUnroll
         for (int c = lane; c < (d >> 2); c += 32) {
             float4 x[RW];
 #pragma unroll
@@ -312,7 +326,7 @@ __device__ __forceinline__ void exact_score_warp_n(const float* const (&xr)[RW],
 }
 
 template <int METRIC, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(RescoreArgs a) {
+__global__ void __launch_bounds__(NT, NT == 256 ? K4_MINBLOCKS : 1) k4_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: keys[cap] u64 | ekeys[cap] u64 | q[dpad] f32 | dedup only: sgrp[cap] i32 | oidx[k] i32 | slead[cap] u8
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k4_rescore_kernel(Resco
     if (m > n_valid || complete) m = n_valid;
     bool certified = false;
     for (;;) {
-        constexpr int RW = 3;    // rows a warp gathers at once (measured: 2 -> 710 us, 3 -> 678 us, 4 -> 690 us at C2)
+        constexpr int RW = K4_RW;    // rows a warp gathers at once (measured: 2 -> 710 us, 3 -> 678 us, 4 -> 690 us at C2)
         for (int i = m_done + RW * wid; i < m; i += RW * nwarp) {
             uint32_t rows[RW];
             const float* xr[RW];
