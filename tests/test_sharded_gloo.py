@@ -38,6 +38,32 @@ class OracleLocalIndex:
         return D, np.where(I >= 0, I + self.off, -1)
 
 
+class TwoPhaseOracleLocalIndex(OracleLocalIndex):
+    """... with the two halves of the two-phase search (IndexFlat.search_begin / search_finish): the "prefilter" scores
+    are the exact ones (eps = 0), in the larger-is-better domain the engine exchanges."""
+    max_batch = 4          # several chunks per call
+
+    def get_option(self, key):
+        assert key == "max_batch"
+        return self.max_batch
+
+    def search_begin(self, xq, k, nb, *, exclude=None):
+        D, I = self.search(np.asarray(xq), k, exclude=exclude)
+        self._held = (D, I)
+        s = np.where(I >= 0, D if self.metric == 0 else -D, -np.inf).astype(np.float32)
+        top = np.full((len(s), nb), -np.inf, np.float32)
+        top[:, :min(nb, k)] = s[:, :nb]
+        return torch.from_numpy(np.concatenate([top, np.zeros((len(s), 1), np.float32)], axis=1))
+
+    def search_finish(self, floor):
+        D, I = self._held
+        s = np.where(I >= 0, D if self.metric == 0 else -D, -np.inf)
+        keep = s >= floor.numpy()[:, None]                       # rows under the floor cannot reach the global top-k
+        self.dropped = getattr(self, "dropped", 0) + int((~keep & (I >= 0)).sum())
+        fill = np.float32(-3.4028235e38 if self.metric == 0 else 3.4028235e38)
+        return np.where(keep, D, fill), np.where(keep, I, -1)
+
+
 def numpy_merge(Dg, Ig, metric):
     """Reference merge: (score, id) order over the concatenated shard lists."""
     Dg, Ig = Dg.numpy(), Ig.numpy()
@@ -75,6 +101,16 @@ def _worker(rank, world, port, metric, with_mask, out):
         Do, Io = oracle.search_seq(xb, xq, k, metric, groups if with_mask else None, excl)
         np.testing.assert_array_equal(I, Io)
         np.testing.assert_allclose(D, Do, rtol=1e-6)
+        # two-phase local search (bounds exchange over gloo, chunks of max_batch queries): same answer, rows dropped
+        tp = ShardedIndexFlat(d, metric, local_factory=TwoPhaseOracleLocalIndex, merge_fn=numpy_merge)
+        assert tp._two_phase
+        tp.add_global(xb)
+        if with_mask:
+            tp.set_groups_global(groups)
+        Dt, It = tp.search(xq, k, exclude=excl)
+        np.testing.assert_array_equal(It, Io)
+        np.testing.assert_allclose(Dt, Do, rtol=1e-6)
+        assert tp.local.dropped > 0
         # sharded merge: this rank keeps the merged rows of its query slice only
         Ds, Is = idx.search(xq, k, exclude=excl, result="slice")
         qlo, qhi = idx.query_slice(nq)

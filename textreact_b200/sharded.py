@@ -175,7 +175,8 @@ class ShardedIndexFlat:
         # otherwise).  TRX_TWO_PHASE=0 / two_phase=False: every shard computes its full local top-k.
         if two_phase is None:
             two_phase = os.environ.get("TRX_TWO_PHASE", "1") != "0"
-        self._two_phase = bool(two_phase) and self._on_cuda and merge_fn is None
+        # (test doubles take part when they implement search_begin / search_finish: the host logic runs on gloo)
+        self._two_phase = bool(two_phase) and ((self._on_cuda and merge_fn is None) or hasattr(self.local, "search_begin"))
 
     @property
     def ntotal(self):
@@ -267,7 +268,7 @@ class ShardedIndexFlat:
             if exclude is not None and not (isinstance(exclude, torch.Tensor) and exclude.is_cuda):
                 exclude = torch.as_tensor(np.ascontiguousarray(exclude, dtype=np.int32)).to(dev)
         kw = {} if attr_below is None else {"attr_below": attr_below}
-        if self._two_phase and self.world > 1 and isinstance(xq, torch.Tensor) and xq.is_cuda:
+        if self._two_phase and self.world > 1 and (not self._on_cuda or (isinstance(xq, torch.Tensor) and xq.is_cuda)):
             D, I = self._local_search_two_phase(xq, k, exclude, kw)
         else:
             D, I = self.local.search(xq, k, exclude=exclude, **kw)   # complete on return (host-synchronised)
@@ -293,17 +294,19 @@ class ShardedIndexFlat:
     def _local_search_two_phase(self, xq, k, exclude, kw):
         mb = int(self.local.get_option("max_batch"))
         nb = bounds_width(k, self.world)
-        if self._xev is not None:      # the bounds exchange shares the export slots with the merge: keep them in order
+        if self._xev is not None and self._on_cuda:      # the bounds exchange shares the export slots with the merge: keep them in order
             torch.cuda.current_stream(xq.device).wait_event(self._xev)
         outs = []
         for q0 in range(0, xq.shape[0], mb):
-            xc = xq[q0:q0 + mb].contiguous()
+            xc = xq[q0:q0 + mb]
+            xc = xc.contiguous() if isinstance(xc, torch.Tensor) else np.ascontiguousarray(xc)
             ec = None if exclude is None else exclude[q0:q0 + mb]
             payload = self.local.search_begin(xc, k, nb, exclude=ec, **kw)
             outs.append(self.local.search_finish(self.exchange_floor(payload, nb, k)))
         if len(outs) == 1:
             return outs[0]
-        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+        cat = torch.cat if isinstance(outs[0][0], torch.Tensor) else np.concatenate
+        return cat([o[0] for o in outs]), cat([o[1] for o in outs])
 
     def exchange_floor(self, payload, nb, k):
         """The bounds exchange: every rank's [nq, nb + 1] payload -> floor[nq], a prefilter score below which no row
@@ -318,7 +321,10 @@ class ShardedIndexFlat:
                                                          _stream_handle(payload.device)), "exchange_floor")
                 return floor
         g = torch.empty((self.world,) + tuple(payload.shape), dtype=payload.dtype, device=payload.device)
-        dist.all_gather_into_tensor(g, payload.contiguous(), group=self.group)
+        if payload.is_cuda:
+            dist.all_gather_into_tensor(g, payload.contiguous(), group=self.group)
+        else:             # gloo (CPU tests of the host logic)
+            dist.all_gather(list(g.unbind(0)), payload.contiguous(), group=self.group)
         return floor_from_payloads(g, nb, k)
 
     def _peer_exchange(self, nq, k, device):
